@@ -1,0 +1,56 @@
+"""
+Ready-printed `ModelSpec`s for the workloads BASELINE.json names (SURVEY.md §8 d) and for the parity tests.
+The expression strings are written the way the reference's examples write them
+(`examples/noisy_lorenz.py:75-87`, `tests/compare_C_and_Python_core.py:36-46`) so that the oracle, which
+compiles the very same strings into the reference C core, sees the same operation order.
+"""
+
+from .modelspec import JumpSpec, ModelSpec
+
+_LORENZ_F = (
+	"10*(y(1)-y(0))",
+	"y(0)*(28-y(2))-y(1)",
+	"y(0)*y(1)-(8.0/3.0)*y(2)",
+)
+
+#: headline workload (BASELINE.json configs[1]): additive noise ⇒ SRA
+lorenz_additive = ModelSpec("lorenz_additive", 3, True, _LORENZ_F, ("0.1", "0.1", "0.1"))
+
+#: the reference's own additive fixture, `tests/compare_C_and_Python_core.py:44` (G = i*0.05)
+lorenz_additive_fixture = ModelSpec("lorenz_additive_fixture", 3, True, _LORENZ_F, ("0.0", "0.05", "0.1"))
+
+#: physics of `examples/noisy_lorenz.py:75-87` (multiplicative ⇒ SRI)
+lorenz_multiplicative = ModelSpec("lorenz_multiplicative", 3, False, _LORENZ_F, ("0.1*y(0)", "0.1*y(1)", "0.1*y(2)"))
+
+#: `examples/noisy_and_jumpy_lorenz.py:36-58`: same SDE plus jumps on component 2 with amplitude |y2|·ξ
+lorenz_jumpy = ModelSpec(
+	"lorenz_jumpy", 3, False, _LORENZ_F, ("0.1*y(0)", "0.1*y(1)", "0.1*y(2)"),
+	jump=JumpSpec(("0.0", "0.0", "0.0 + fabs(y(2))*xi")),
+)
+
+#: geometric Brownian motion, closed-form moments (SURVEY §8 d config 3 i)
+gbm = ModelSpec("gbm", 1, False, ("0.05*y(0)",), ("0.2*y(0)",))
+
+#: GBM with control parameters (exercises set_parameters, reference `_jitcsde.py:465-484`)
+gbm_pars = ModelSpec("gbm_pars", 1, False, ("mu*y(0)",), ("sigma*y(0)",), control_pars=("mu", "sigma"))
+
+#: stochastic Duffing oscillator (SURVEY §8 d config 3 ii): δ=0.3 α=-1 β=1 σ=0.3
+duffing = ModelSpec(
+	"duffing", 2, False,
+	("y(1)", "-0.3*y(1)-(-1.0)*y(0)-1.0*(y(0)*y(0)*y(0))"),
+	("0.0", "0.3*y(0)"),
+)
+
+#: Ornstein–Uhlenbeck pair: contracting, so per-trajectory parity is meaningful at long horizons
+ou = ModelSpec("ou", 2, True, ("-1.0*y(0)", "-0.5*(y(1)-1.0)"), ("0.3", "0.2"))
+
+#: time-dependent additive noise (exercises the g(t+h) / g(t) evaluation order of `jitced_template.c:476,485`)
+ou_timedep = ModelSpec("ou_timedep", 2, True, ("-1.0*y(0)+t", "-0.5*(y(1)-1.0)"), ("0.3*(1.0+t)", "0.2/(1.0+t*t)"))
+
+#: scalar validation SDE of `tests/validation.py:21-32` without the exponential (polynomial part only)
+cubic = ModelSpec("cubic", 1, True, ("-(y(0)*y(0)*y(0))+4*y(0)+y(0)*y(0)",), ("3.0",))
+
+ALL = {m.name: m for m in (
+	lorenz_additive, lorenz_additive_fixture, lorenz_multiplicative, lorenz_jumpy,
+	gbm, gbm_pars, duffing, ou, ou_timedep, cubic,
+)}
