@@ -62,6 +62,7 @@ class RefIntegrator:
 		if p > self.decrease_threshold:
 			self.dt = actual_dt * max(self.safety_factor * p ** (-1 / self.q), self.min_factor)
 			if self.dt < self.min_step:
+				self.rejected += 1  # the failing attempt is a rejected one (bookkeeping only; the reference keeps no counters)
 				raise UnsuccessfulIntegration("step size below min_step")
 			return False
 		if p <= self.increase_threshold:
