@@ -1,0 +1,57 @@
+// Device-memory layout of one ensemble (B trajectories of an n-dimensional SDE) and the POD handed to kernels.
+//
+// Everything a trajectory owns is stored structure-of-arrays with the trajectory index fastest, so that a warp whose
+// 32 lanes hold 32 consecutive trajectories reads and writes 256 contiguous bytes per double field:
+//
+//   y        [n][B]      state                                   (reference: sde_integrator.state, template:29)
+//   t, dt    [B]         time, controller step size              (template:30; _jitcsde.py self.dt)
+//   new_y, err [n][B], new_t [B]   last proposal                 (template:31-33) — only the single-step surface uses them
+//   q_h      [D][B]      noise memory: length of item d          (template:15-21, as a bounded array instead of a list;
+//   q_w      [D][2n][B]  its DW (rows 0..n-1) and DZ (n..2n-1)    item 0 always starts at the current time)
+//   q_count, q_cursor [B]
+//   mt       [B][156] uint4   generator state, one contiguous 2496-byte record per trajectory (random_numbers.c:31-38);
+//                             positions of different trajectories drift apart (rejections), so records are lane-private
+//   mt_chunk [B]         next 4-word chunk (the reference's `pos` / 4)
+//   par      [P] or [P][B]    control parameters (template:34-36)
+//   status   [B]; accepted, rejected [B]
+//   jump scheduling: next_jump [B], jump_set [B], tape_pos [B], tape taus/xis [B][L]
+#pragma once
+
+#include <stdint.h>
+
+namespace jsde {
+
+struct Controller {
+	double atol, rtol, min_step, max_step, dec_thr, inc_thr, safety, max_factor, min_factor;
+	double shrink_exp;  // -1/q        (_jitcsde.py:587)
+	double grow_exp;    // -1/(q+1)    (_jitcsde.py:592)
+};
+
+struct CallTotals {
+	unsigned long long accepted, rejected, fresh_draws, jumps;
+	long long n_min_step, n_overflow;
+	int max_depth;
+};
+
+struct EnsembleView {
+	int64_t B;
+	int D;  // noise capacity (items)
+	double *y, *t, *dt;
+	double *new_y, *err, *new_t;
+	double *q_h, *q_w;
+	int *q_count, *q_cursor;
+	uint4 *mt;
+	int *mt_chunk;
+	const double *par;
+	int64_t par_stride;  // 0: shared, B: per trajectory
+	int *status;
+	unsigned long long *accepted, *rejected;
+	double *next_jump;
+	unsigned char *jump_set;
+	long long *tape_pos;
+	const double *taus, *xis;
+	long long tape_len;
+	CallTotals *totals;
+};
+
+}  // namespace jsde

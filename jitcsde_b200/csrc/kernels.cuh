@@ -1,0 +1,334 @@
+// Kernels: the fused integrate loop (one trajectory per lane, whole call in one launch), the single-step surface that
+// mirrors the reference core call by call, and the small utilities (seeding, layout transposes, moments, FP64 peak).
+#pragma once
+
+#include "stepper.cuh"
+
+namespace jsde {
+
+constexpr int BLOCK = 128;
+
+// ---- totals: warp-reduce, one atomic per warp -------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+__device__ __forceinline__ int warp_max(int v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+
+__device__ __forceinline__ void add_totals(CallTotals *tot, unsigned long long acc, unsigned long long rej, unsigned long long fresh,
+	unsigned long long jumps, int min_step, int overflow, int depth)
+{
+	acc = warp_sum(acc);
+	rej = warp_sum(rej);
+	fresh = warp_sum(fresh);
+	jumps = warp_sum(jumps);
+	const unsigned long long ms = warp_sum((unsigned long long)min_step);
+	const unsigned long long ov = warp_sum((unsigned long long)overflow);
+	depth = warp_max(depth);
+	if ((threadIdx.x & 31) == 0) {
+		if (acc) atomicAdd(&tot->accepted, acc);
+		if (rej) atomicAdd(&tot->rejected, rej);
+		if (fresh) atomicAdd(&tot->fresh_draws, fresh);
+		if (jumps) atomicAdd(&tot->jumps, jumps);
+		if (ms) atomicAdd((unsigned long long *)&tot->n_min_step, ms);
+		if (ov) atomicAdd((unsigned long long *)&tot->n_overflow, ov);
+		if (depth) atomicMax(&tot->max_depth, depth);
+	}
+}
+
+// ---- the hot path -------------------------------------------------------------------------------------------------
+// jitcsde.integrate (_jitcsde.py:597-630) and, with a tape, jitcsde_jump.integrate (:693-700) for every trajectory.
+// Each loop iteration is one attempted step of every lane that still has work; choosing the next target and applying
+// a jump are folded into the same loop so that lanes which jump do not serialise the warp.
+template <class Model>
+__global__ void __launch_bounds__(BLOCK) k_integrate(EnsembleView e, Controller c, double target, int use_tape)
+{
+	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+	const bool live = k < e.B;
+	unsigned long long acc = 0, rej = 0, jumps = 0, fresh = 0;
+	int failed_min = 0, failed_ovf = 0, depth = 0;
+	if (live) {
+		Lane<Model> L(e, k);
+		L.load();
+		if (L.status == TRAJ_MIN_STEP)
+			L.status = TRAJ_OK;  // the reference raises once per call and lets the caller carry on (:569-579)
+		L.cursor = 0;
+		double next_jump = 0.0;
+		bool jump_set = false;
+		long long tape_pos = 0;
+		if (Model::HAS_JUMP && use_tape) {
+			next_jump = e.next_jump[k];
+			jump_set = e.jump_set[k] != 0;
+			tape_pos = e.tape_pos[k];
+		}
+		bool need_target = true, to_jump = false;
+		double tgt = target;
+		while (L.status == TRAJ_OK) {
+			if (need_target) {
+				tgt = target;
+				to_jump = false;
+				if (Model::HAS_JUMP && use_tape) {
+					if (!jump_set) {  // next_jump property (:682-687): t + IJI(t, y)
+						const double wait = tape_pos < e.tape_len ? e.taus[k * e.tape_len + tape_pos] : __longlong_as_double(0x7ff0000000000000LL);
+						next_jump = L.t + wait;
+						jump_set = true;
+					}
+					if (next_jump < target) {
+						tgt = next_jump;
+						to_jump = true;
+					}
+				}
+				need_target = false;
+				if (L.t >= tgt) {  // integrate() with nothing to do (:614)
+					if (!to_jump)
+						break;
+					double change[Model::N];
+					Model::jump(L.t, L.y, e.xis[k * e.tape_len + tape_pos], L.par, change);
+#pragma unroll
+					for (int i = 0; i < Model::N; i++)
+						L.y[i] += change[i];
+					tape_pos++;
+					jumps++;
+					jump_set = false;
+					need_target = true;
+					continue;
+				}
+			}
+			double actual_dt;
+			bool last;
+			if (L.t + L.dt < tgt) {
+				actual_dt = L.dt;
+				last = false;
+			} else {
+				actual_dt = tgt - L.t;
+				last = true;
+			}
+			if (!L.propose(actual_dt))
+				break;
+			const int verdict = L.adjust_step(c, actual_dt);
+			if (verdict == 1) {
+				L.commit();
+				acc++;
+				if (last) {
+					if (!to_jump)
+						break;
+					double change[Model::N];  // apply_jump(amp(time, state)) (:696-698)
+					Model::jump(L.t, L.y, e.xis[k * e.tape_len + tape_pos], L.par, change);
+#pragma unroll
+					for (int i = 0; i < Model::N; i++)
+						L.y[i] += change[i];
+					tape_pos++;
+					jumps++;
+					jump_set = false;
+					need_target = true;
+				}
+			} else {
+				rej++;
+				if (verdict < 0)
+					L.status = TRAJ_MIN_STEP;
+			}
+		}
+		L.store();
+		if (Model::HAS_JUMP && use_tape) {
+			e.next_jump[k] = next_jump;
+			e.jump_set[k] = jump_set ? 1 : 0;
+			e.tape_pos[k] = tape_pos;
+		}
+		e.accepted[k] += acc;
+		e.rejected[k] += rej;
+		fresh = L.fresh;
+		depth = L.max_depth;
+		failed_min = L.status == TRAJ_MIN_STEP;
+		failed_ovf = L.status == TRAJ_NOISE_OVERFLOW;
+	}
+	add_totals(e.totals, acc, rej, fresh, jumps, failed_min, failed_ovf, depth);
+}
+
+// ---- single-step surface (reference core methods, one launch each) ---------------------------------------------
+template <class Model>
+__global__ void __launch_bounds__(BLOCK) k_get_next_step(EnsembleView e, const double *h)
+{
+	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+	if (k >= e.B)
+		return;
+	Lane<Model> L(e, k);
+	L.load();
+	if (L.status == TRAJ_NOISE_OVERFLOW)
+		return;
+	if (L.propose(h[k]))
+		L.store_proposal();
+	L.store();
+}
+
+template <class Model>
+__global__ void __launch_bounds__(BLOCK) k_get_p(EnsembleView e, double atol, double rtol, double *p)
+{
+	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+	if (k >= e.B)
+		return;
+	Lane<Model> L(e, k);
+	L.load_proposal();
+	p[k] = L.error_ratio(atol, rtol);
+}
+
+template <class Model>
+__global__ void __launch_bounds__(BLOCK) k_accept_step(EnsembleView e, const unsigned char *mask)
+{
+	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+	if (k >= e.B || (mask && !mask[k]))
+		return;
+	Lane<Model> L(e, k);
+	L.load();
+	L.load_proposal();
+	L.commit();
+	L.store();
+}
+
+template <class Model>
+__global__ void __launch_bounds__(BLOCK) k_pin_noise(EnsembleView e, unsigned number, double step)
+{
+	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+	if (k >= e.B)
+		return;
+	Lane<Model> L(e, k);
+	L.load();
+	if (L.status == TRAJ_NOISE_OVERFLOW)
+		return;
+	L.pin(number, step);
+	L.store();
+}
+
+// rk_gauss stream of every trajectory: out [B][pairs][2]
+template <class Model>
+__global__ void __launch_bounds__(BLOCK) k_draw_gauss(EnsembleView e, double scale, int pairs, double *out)
+{
+	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+	if (k >= e.B)
+		return;
+	Lane<Model> L(e, k);
+	L.load();
+	for (int j = 0; j < pairs; j++) {
+		double x1, x2, r2;
+		while (!polar_candidate(L.next_words(), x1, x2, r2)) {
+		}
+		const double f = scale * polar_radius_factor(r2);
+		out[(k * pairs + j) * 2] = x1 * f;
+		out[(k * pairs + j) * 2 + 1] = x2 * f;
+	}
+	L.store();
+}
+
+// ---- model-independent helpers ------------------------------------------------------------------------------------
+__global__ void k_seed(uint4 *mt, int *mt_chunk, const uint32_t *seeds, int64_t B)
+{
+	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= B)
+		return;
+	mt_seed(mt + k * MT_CHUNKS, seeds[k]);
+	mt_chunk[k] = 0;
+}
+
+// rows [B][n] (trajectory-major, host layout)  <->  cols [n][B] (device layout)
+__global__ void k_rows_to_cols(const double *rows, double *cols, int64_t B, int n, int accumulate)
+{
+	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= B * n)
+		return;
+	const int64_t k = idx / n;
+	const int i = (int)(idx - k * n);
+	if (accumulate)
+		cols[(int64_t)i * B + k] += rows[idx];
+	else
+		cols[(int64_t)i * B + k] = rows[idx];
+}
+
+__global__ void k_cols_to_rows(const double *cols, double *rows, int64_t B, int n)
+{
+	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= B * n)
+		return;
+	const int64_t k = idx / n;
+	const int i = (int)(idx - k * n);
+	rows[idx] = cols[(int64_t)i * B + k];
+}
+
+__global__ void k_fill(double *dst, double value, int64_t count)
+{
+	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx < count)
+		dst[idx] = value;
+}
+
+// acc[0] += #ok, acc[1+i] += sum (y_i - shift_i), acc[1+n+i] += sum (y_i - shift_i)^2 over trajectories with status OK
+__global__ void k_moments(const double *y, const int *status, int64_t B, int n, const double *shift, double *acc)
+{
+	extern __shared__ double sh[];  // [blockDim.x / 32][1 + 2n]
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	const int width = 1 + 2 * n;
+	for (int f = 0; f < width; f++) {
+		double part = 0.0;
+		for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < B; k += (int64_t)gridDim.x * blockDim.x) {
+			if (status[k] != TRAJ_OK)
+				continue;
+			if (f == 0)
+				part += 1.0;
+			else {
+				const int i = (f - 1) % n;
+				const double d = y[(int64_t)i * B + k] - shift[i];
+				part += (f <= n) ? d : d * d;
+			}
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+			part += __shfl_xor_sync(0xffffffffu, part, o);
+		if (lane == 0)
+			sh[warp * width + f] = part;
+	}
+	__syncthreads();
+	for (int f = threadIdx.x; f < width; f += blockDim.x) {
+		double s = 0.0;
+		for (int w = 0; w < nw; w++)
+			s += sh[w * width + f];
+		atomicAdd(&acc[f], s);
+	}
+}
+
+// FP64 peak: 8 independent dependent-chains of DFMA per thread
+__global__ void k_dfma_peak(double *sink, int iters)
+{
+	double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+	const double m = 0.999999, b = 1e-7;
+	for (int i = 0; i < iters; i++) {
+		a0 = __fma_rn(a0, m, b); a1 = __fma_rn(a1, m, b); a2 = __fma_rn(a2, m, b); a3 = __fma_rn(a3, m, b);
+		a4 = __fma_rn(a4, m, b); a5 = __fma_rn(a5, m, b); a6 = __fma_rn(a6, m, b); a7 = __fma_rn(a7, m, b);
+	}
+	const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+	if (s == 123.456)
+		sink[0] = s;
+}
+
+__global__ void k_debug_log(const double *x, double *out, int64_t count)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count)
+		out[i] = jsde_log(x[i]);
+}
+
+__global__ void k_debug_pow(const double *x, double yexp, double *out, int64_t count)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count)
+		out[i] = jsde_pow(x[i], yexp);
+}
+
+}  // namespace jsde

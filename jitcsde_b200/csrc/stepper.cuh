@@ -1,0 +1,383 @@
+// One trajectory per lane: noise memory, Rößler SRA1 / SRIW1 proposal, error ratio, commit and the step-size
+// controller, with the trajectory's state held in registers for the whole call.
+//
+// Arithmetic keeps the reference's expression shapes (operation order, true divisions, no fused multiply-adds
+// outside the libm restatements) so that the result equals the strict-IEEE build of the reference bit for bit:
+//   noise memory ........ reference jitcsde/jitced_template.c:170-250  (append_noise, Brownian_bridge, get_noise)
+//   iterated integrals .. jitced_template.c:269-291                     (get_I)
+//   SRI / SRA ........... jitced_template.c:408-464 / :466-494          (get_next_step)
+//   error ratio ......... jitced_template.c:502-526                     (get_p)
+//   commit .............. jitced_template.c:528-536                     (accept_step)
+//   controller .......... reference jitcsde/_jitcsde.py:569-595         (_control_for_min_step, _adjust_step_size)
+// This translation unit must be compiled with -fmad=false.
+#pragma once
+
+#include "ensemble.cuh"
+#include "gauss.cuh"
+#include "mt19937.cuh"
+
+namespace jsde {
+
+enum { TRAJ_OK = 0, TRAJ_MIN_STEP = 1, TRAJ_NOISE_OVERFLOW = 2 };
+
+template <class Model>
+struct Lane {
+	static constexpr int N = Model::N;
+	static constexpr bool ADDITIVE = Model::ADDITIVE;
+	static constexpr int NP = Model::NPAR;
+
+	const EnsembleView &e;
+	const int64_t k;
+	uint4 *S;
+
+	double y[N], t, dt;
+	double ny[N], er[N], nt;  // last proposal
+	double par[NP > 0 ? NP : 1];
+	int count, cursor, chunk, status;
+	unsigned fresh;
+	int max_depth;
+
+	__device__ __forceinline__ Lane(const EnsembleView &view, int64_t index)
+		: e(view), k(index), S(view.mt + index * MT_CHUNKS), fresh(0), max_depth(0) {}
+
+	// ---- global-memory accessors ---------------------------------------------------------------------------
+	__device__ __forceinline__ double &qh(int d) const { return e.q_h[(int64_t)d * e.B + k]; }
+	__device__ __forceinline__ double &qw(int d, int c) const { return e.q_w[((int64_t)d * (2 * N) + c) * e.B + k]; }
+
+	__device__ __forceinline__ void load()
+	{
+#pragma unroll
+		for (int i = 0; i < N; i++)
+			y[i] = e.y[(int64_t)i * e.B + k];
+		t = e.t[k];
+		dt = e.dt[k];
+		count = e.q_count[k];
+		cursor = e.q_cursor[k];
+		chunk = e.mt_chunk[k];
+		status = e.status[k];
+#pragma unroll
+		for (int i = 0; i < NP; i++)
+			par[i] = e.par[e.par_stride ? (int64_t)i * e.B + k : i];
+	}
+
+	__device__ __forceinline__ void store() const
+	{
+#pragma unroll
+		for (int i = 0; i < N; i++)
+			e.y[(int64_t)i * e.B + k] = y[i];
+		e.t[k] = t;
+		e.dt[k] = dt;
+		e.q_count[k] = count;
+		e.q_cursor[k] = cursor;
+		e.mt_chunk[k] = chunk;
+		e.status[k] = status;
+	}
+
+	__device__ __forceinline__ void load_proposal()
+	{
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			ny[i] = e.new_y[(int64_t)i * e.B + k];
+			er[i] = e.err[(int64_t)i * e.B + k];
+		}
+		nt = e.new_t[k];
+	}
+
+	__device__ __forceinline__ void store_proposal() const
+	{
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			e.new_y[(int64_t)i * e.B + k] = ny[i];
+			e.err[(int64_t)i * e.B + k] = er[i];
+		}
+		e.new_t[k] = nt;
+	}
+
+	// ---- generator ---------------------------------------------------------------------------------------------
+	__device__ __forceinline__ uint4 next_words()
+	{
+		uint4 w = mt_consume_chunk(S, chunk);
+		chunk = mt_wrap(chunk + 1);
+		w.x = mt_temper(w.x);
+		w.y = mt_temper(w.y);
+		w.z = mt_temper(w.z);
+		w.w = mt_temper(w.w);
+		return w;
+	}
+
+	// get_gauss (template:145-154): components in order, one accepted pair each.  The per-component rejection loops
+	// are flattened into one loop with a per-lane component cursor, so a warp iterates max-over-lanes of the *total*
+	// number of candidates instead of the sum of per-component maxima; log/div/sqrt run after it, convergent.
+	__device__ __forceinline__ void draw(double scale, double (&gW)[N], double (&gZ)[N])
+	{
+		double r2s[N];
+		int c = 0;
+		while (c < N) {
+			double x1, x2, r2;
+			const bool ok = polar_candidate(next_words(), x1, x2, r2);
+			if (ok) {
+#pragma unroll
+				for (int i = 0; i < N; i++)
+					if (i == c) {
+						gW[i] = x1;
+						gZ[i] = x2;
+						r2s[i] = r2;
+					}
+				c++;
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			const double f = scale * polar_radius_factor(r2s[i]);
+			gW[i] *= f;
+			gZ[i] *= f;
+		}
+	}
+
+	// ---- noise memory -------------------------------------------------------------------------------------------
+	// get_noise (template:204-250).  At most one fresh item is drawn per call: after a bridge or an append the item
+	// at the cursor has exactly the missing length, so the reference's loop consumes it and stops.
+	__device__ __forceinline__ bool collect_noise(double h, double (&W)[N], double (&Z)[N])
+	{
+		bool started = false;
+		double need = h;
+		int cur = 0;
+		while (need != 0.0 && cur < count) {
+			const double hq = qh(cur);
+			if (!(hq <= need))
+				break;
+			if (started) {
+#pragma unroll
+				for (int i = 0; i < N; i++) {
+					W[i] += qw(cur, i);
+					Z[i] += qw(cur, N + i);
+				}
+			} else {
+				started = true;
+#pragma unroll
+				for (int i = 0; i < N; i++) {
+					W[i] = qw(cur, i);
+					Z[i] = qw(cur, N + i);
+				}
+			}
+			need -= hq;
+			cur++;
+		}
+		if (need != 0.0) {
+			if (count >= e.D) {
+				status = TRAJ_NOISE_OVERFLOW;
+				return false;
+			}
+			const bool bridging = cur < count;
+			double h_exc = 0.0, factor = 0.0, scale;
+			if (bridging) {  // Brownian_bridge (template:178-202)
+				const double h_item = qh(cur);
+				h_exc = h_item - need;
+				factor = h_exc / h_item;
+				scale = sqrt(factor * need);
+			} else  // append_noise (template:170-176)
+				scale = sqrt(need);
+			double gW[N], gZ[N];
+			draw(scale, gW, gZ);
+			fresh++;
+			if (bridging) {
+				for (int d = count - 1; d > cur; d--) {  // make room behind the cursor (the reference relinks its list)
+					qh(d + 1) = qh(d);
+					for (int c = 0; c < 2 * N; c++)
+						qw(d + 1, c) = qw(d, c);
+				}
+#pragma unroll
+				for (int i = 0; i < N; i++) {
+					const double w1 = qw(cur, i), z1 = qw(cur, N + i);
+					const double w2 = gW[i] + w1 * factor, z2 = gZ[i] + z1 * factor;
+					gW[i] = w1 - w2;
+					gZ[i] = z1 - z2;
+					qw(cur + 1, i) = w2;
+					qw(cur + 1, N + i) = z2;
+				}
+				qh(cur + 1) = h_exc;
+			}
+			qh(cur) = need;
+#pragma unroll
+			for (int i = 0; i < N; i++) {
+				qw(cur, i) = gW[i];
+				qw(cur, N + i) = gZ[i];
+			}
+			count++;
+			if (started) {
+#pragma unroll
+				for (int i = 0; i < N; i++) {
+					W[i] += gW[i];
+					Z[i] += gZ[i];
+				}
+			} else {
+				started = true;
+#pragma unroll
+				for (int i = 0; i < N; i++) {
+					W[i] = gW[i];
+					Z[i] = gZ[i];
+				}
+			}
+			cur++;
+		}
+		if (!started) {
+#pragma unroll
+			for (int i = 0; i < N; i++)
+				W[i] = Z[i] = 0.0;
+		}
+		cursor = cur;
+		max_depth = count > max_depth ? count : max_depth;
+		return true;
+	}
+
+	// pin_noise (template:252-267): append `number` fresh items of length `step`
+	__device__ __forceinline__ void pin(unsigned number, double step)
+	{
+		for (unsigned j = 0; j < number; j++) {
+			if (count >= e.D) {
+				status = TRAJ_NOISE_OVERFLOW;
+				return;
+			}
+			double gW[N], gZ[N];
+			draw(sqrt(step), gW, gZ);
+			qh(count) = step;
+#pragma unroll
+			for (int i = 0; i < N; i++) {
+				qw(count, i) = gW[i];
+				qw(count, N + i) = gZ[i];
+			}
+			count++;
+		}
+		if (number)
+			cursor = count - 1;  // template:173: current_noise = the newest item, so an accept_step right after keeps only it
+		max_depth = count > max_depth ? count : max_depth;
+	}
+
+	// ---- proposal (get_next_step) ---------------------------------------------------------------------------------
+	__device__ __forceinline__ bool propose(double h)
+	{
+		double I1[N], DZ[N], I10[N];
+		if (!collect_noise(h, I1, DZ))
+			return false;
+		double arg[N], fh1[N], fh2[N], g1[N], g2[N];
+		if constexpr (!ADDITIVE) {
+			double I11s[N], I111[N], g3[N], g4[N];
+			const double sqh = sqrt(h);
+#pragma unroll
+			for (int i = 0; i < N; i++) {  // template:283-290
+				I11s[i] = (I1[i] * I1[i] - h) * 0.5 / sqh;
+				I111[i] = (I1[i] * I1[i] * I1[i] - 3 * h * I1[i]) * (1. / 6.);
+				I10[i] = (I1[i] + DZ[i] * (1. / 1.7320508075688772)) * (h / 2.);
+			}
+			Model::drift(t, y, h, par, fh1);
+			Model::diffusion(t, y, par, g1);
+#pragma unroll
+			for (int i = 0; i < N; i++)
+				arg[i] = y[i] + 0.75 * fh1[i] + 1.5 * g1[i] * I10[i] / h;
+			Model::drift(t + 0.75 * h, arg, h, par, fh2);
+#pragma unroll
+			for (int i = 0; i < N; i++)
+				arg[i] = y[i] + 0.25 * fh1[i] + 0.5 * g1[i] * sqh;
+			Model::diffusion(t + 0.25 * h, arg, par, g2);
+#pragma unroll
+			for (int i = 0; i < N; i++)
+				arg[i] = y[i] + fh1[i] - g1[i] * sqh;
+			Model::diffusion(t + h, arg, par, g3);
+#pragma unroll
+			for (int i = 0; i < N; i++)
+				arg[i] = y[i] + 0.25 * fh1[i] + sqh * (-5 * g1[i] + 3 * g2[i] + 0.5 * g3[i]);
+			Model::diffusion(t + 0.25 * h, arg, par, g4);
+#pragma unroll
+			for (int i = 0; i < N; i++) {  // template:447-464
+				const double E_N = (1. / h / 3.) * (
+					+ (6 * I10[i] - 6 * I111[i]) * g1[i]
+					+ (-4 * I10[i] + 5 * I111[i]) * g2[i]
+					+ (-2 * I10[i] - 2 * I111[i]) * g3[i]
+					+ (3 * I111[i]) * g4[i]);
+				ny[i] = y[i] + E_N + (1. / 3.) * (
+					fh1[i] + 2 * fh2[i]
+					+ (-3 * I1[i] - 3 * I11s[i]) * g1[i]
+					+ (4 * I1[i] + 4 * I11s[i]) * g2[i]
+					+ (2 * I1[i] - I11s[i]) * g3[i]);
+				const double E_D = (fh2[i] - fh1[i]) / 6;
+				er[i] = fabs(E_D) + fabs(E_N);
+			}
+		} else {
+#pragma unroll
+			for (int i = 0; i < N; i++)
+				I10[i] = (I1[i] + DZ[i] * (1. / 1.7320508075688772)) * (h / 2.);
+			Model::drift(t, y, h, par, fh1);
+			Model::diffusion(t + h, y, par, g1);
+#pragma unroll
+			for (int i = 0; i < N; i++)
+				arg[i] = y[i] + 0.75 * fh1[i] + 0.5 * g1[i] * I10[i] / h;
+			Model::drift(t + 0.75 * h, arg, h, par, fh2);
+			Model::diffusion(t, y, par, g2);
+#pragma unroll
+			for (int i = 0; i < N; i++) {  // template:487-494
+				const double E_N = I10[i] / h * (g2[i] - g1[i]);
+				ny[i] = y[i] + E_N + (1. / 3.) * (fh1[i] + 2 * fh2[i]) + I1[i] * g1[i];
+				const double E_D = (fh2[i] - fh1[i]) / 6;
+				er[i] = fabs(E_D) + fabs(E_N);
+			}
+		}
+		nt = t + h;
+		return true;
+	}
+
+	// get_p (template:502-526): a 0/0 component is skipped, a NaN never wins the comparison
+	__device__ __forceinline__ double error_ratio(double atol, double rtol) const
+	{
+		double worst = 0.0;
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			const double tol = atol + rtol * fabs(ny[i]);
+			if (er[i] != 0.0 || tol != 0.0) {
+				const double x = er[i] / tol;
+				if (x > worst)
+					worst = x;
+			}
+		}
+		return worst;
+	}
+
+	// accept_step (template:528-536): commit the proposal, drop the consumed items
+	__device__ __forceinline__ void commit()
+	{
+#pragma unroll
+		for (int i = 0; i < N; i++)
+			y[i] = ny[i];
+		t = nt;
+		const int rest = count - cursor;
+		if (cursor > 0)
+			for (int d = 0; d < rest; d++) {
+				qh(d) = qh(d + cursor);
+				for (int c = 0; c < 2 * N; c++)
+					qw(d, c) = qw(d + cursor, c);
+			}
+		count = rest;
+		cursor = 0;
+	}
+
+	// _adjust_step_size (_jitcsde.py:581-595).  Returns 1 accepted, 0 rejected, -1 rejected with dt < min_step.
+	// Python's max(a,b)/min(a,b) return b only if it compares strictly greater/smaller; kept literally.
+	__device__ __forceinline__ int adjust_step(const Controller &c, double actual_dt)
+	{
+		const double p = error_ratio(c.atol, c.rtol);
+		if (p > c.dec_thr) {
+			const double pw = (p > 1.7976931348623157e308) ? 0.0 : jsde_pow(p, c.shrink_exp);  // inf ** negative = 0.0
+			const double shrink = c.safety * pw;
+			dt = actual_dt * (c.min_factor > shrink ? c.min_factor : shrink);
+			return dt < c.min_step ? -1 : 0;
+		}
+		if (p <= c.inc_thr) {
+			const double factor = (p != 0.0) ? c.safety * jsde_pow(p, c.grow_exp) : c.max_factor;
+			const double sug = actual_dt * (c.max_factor < factor ? c.max_factor : factor);
+			const double capped = c.max_step < sug ? c.max_step : sug;
+			dt = capped > dt ? capped : dt;
+		}
+		return 1;
+	}
+};
+
+}  // namespace jsde
