@@ -11,7 +11,8 @@
 //   q_count, q_cursor [B]
 //   mt       [B][156] uint4   generator state, one contiguous 2496-byte record per trajectory (random_numbers.c:31-38);
 //                             positions of different trajectories drift apart (rejections), so records are lane-private
-//   mt_chunk [B]         next 4-word chunk (the reference's `pos` / 4)
+//   mt_chunk [B]         next 4-word chunk to generate (the reference's `pos` / 4, running ahead by the queued pairs)
+//   rng_spill [CAP][3][B], rng_level [B]   polar pairs generated but not yet consumed (warp_rng.cuh), kept between launches
 //   par      [P] or [P][B]    control parameters (template:34-36)
 //   status   [B]; accepted, rejected [B]
 //   jump scheduling: next_jump [B], jump_set [B], tape_pos [B], tape taus/xis [B][L]
@@ -42,6 +43,8 @@ struct EnsembleView {
 	int *q_count, *q_cursor;
 	uint4 *mt;
 	int *mt_chunk;
+	double *rng_spill;  // [CAP][3][B] accepted-but-unconsumed pairs (x1, x2, r2) between kernel launches
+	int *rng_level;     // [B]
 	const double *par;
 	int64_t par_stride;  // 0: shared, B: per trajectory
 	int *status;

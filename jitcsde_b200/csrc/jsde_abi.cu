@@ -104,6 +104,7 @@ int reset_integrator(jsde_handle *h)
 	CU(cudaMemsetAsync(h->v.tape_pos, 0, B * sizeof(long long), h->stream));
 	CU(cudaMemsetAsync(h->v.new_y, 0, (size_t)B * Model::N * sizeof(double), h->stream));
 	CU(cudaMemsetAsync(h->v.err, 0, (size_t)B * Model::N * sizeof(double), h->stream));
+	CU(cudaMemsetAsync(h->v.rng_level, 0, B * sizeof(int), h->stream));
 	k_seed<<<grid_for(B, 64), 64, 0, h->stream>>>(h->v.mt, h->v.mt_chunk, h->seeds, B);
 	CU(cudaGetLastError());
 	return JSDE_OK;
@@ -179,6 +180,7 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	ALLOC(v.q_h, (int64_t)h->D * B); ALLOC(v.q_w, (int64_t)h->D * 2 * n * B);
 	ALLOC(v.q_count, B); ALLOC(v.q_cursor, B);
 	ALLOC(v.mt, B * MT_CHUNKS); ALLOC(v.mt_chunk, B);
+	ALLOC(v.rng_spill, (int64_t)WarpRng<Model::N>::CAP * 3 * B); ALLOC(v.rng_level, B);
 	ALLOC(v.status, B); ALLOC(v.accepted, B); ALLOC(v.rejected, B);
 	ALLOC(v.next_jump, B); ALLOC(v.jump_set, B); ALLOC(v.tape_pos, B);
 	ALLOC(v.totals, 1);
@@ -202,8 +204,6 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	if ((rc = reset_integrator(h))) return bail(rc);
 	if ((err = cudaStreamSynchronize(h->stream)) != cudaSuccess)
 		return bail(fail(JSDE_E_CUDA, cudaGetErrorString(err)));
-	// no shared memory is used by the lane kernels: give the whole unified array to L1 (generator records, noise memory)
-	cudaFuncSetAttribute(k_integrate<Model>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
 	*out = h;
 	return JSDE_OK;
 }
@@ -312,7 +312,7 @@ int jsde_pin_noise(jsde_t *h, unsigned number, double step)
 		return fail(JSDE_E_ARG, "Wrong input.");
 	int rc = bind(h);
 	if (rc) return rc;
-	k_pin_noise<Model><<<grid_for(h->B, BLOCK), BLOCK, 0, h->stream>>>(h->v, number, step);
+	k_pin_noise<Model><<<grid_for(h->B, BLOCK), BLOCK, rng_smem_bytes<Model>(), h->stream>>>(h->v, number, step);
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(h->stream));
 	return JSDE_OK;
@@ -324,7 +324,7 @@ static int integrate_common(jsde_t *h, double target_time, int use_tape, jsde_st
 		return fail(JSDE_E_ARG, "Wrong input. (target time is NaN)");
 	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
 	CU(cudaEventRecord(h->ev0, h->stream));
-	k_integrate<Model><<<grid_for(h->B, BLOCK), BLOCK, 0, h->stream>>>(h->v, h->ctrl, target_time, use_tape);
+	k_integrate<Model><<<grid_for(h->B, BLOCK), BLOCK, rng_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape);
 	CU(cudaGetLastError());
 	return finish_call(h, stats_host, 1);
 }
@@ -424,7 +424,7 @@ int jsde_get_next_step(jsde_t *h, const double *h_host)
 	int rc = bind(h);
 	if (rc) return rc;
 	CU(cudaMemcpyAsync(h->staging, h_host, h->B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-	k_get_next_step<Model><<<grid_for(h->B, BLOCK), BLOCK, 0, h->stream>>>(h->v, h->staging);
+	k_get_next_step<Model><<<grid_for(h->B, BLOCK), BLOCK, rng_smem_bytes<Model>(), h->stream>>>(h->v, h->staging);
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(h->stream));
 	return JSDE_OK;
@@ -494,7 +494,7 @@ int jsde_draw_gauss_debug(jsde_t *h, double scale, int pairs, double *out_host)
 	double *out = nullptr;
 	const size_t count = (size_t)h->B * pairs * 2;
 	CU(cudaMalloc(&out, count * sizeof(double) + 16));
-	k_draw_gauss<Model><<<grid_for(h->B, BLOCK), BLOCK, 0, h->stream>>>(h->v, scale, pairs, out);
+	k_draw_gauss<Model><<<grid_for(h->B, BLOCK), BLOCK, rng_smem_bytes<Model>(), h->stream>>>(h->v, scale, pairs, out);
 	cudaError_t err = cudaGetLastError();
 	if (err == cudaSuccess) err = cudaMemcpyAsync(out_host, out, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
 	if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);

@@ -47,33 +47,55 @@ __device__ __forceinline__ void add_totals(CallTotals *tot, unsigned long long a
 }
 
 // ---- the hot path -------------------------------------------------------------------------------------------------
+// Shared memory: one set of generator FIFOs per warp (warp_rng.cuh).
+template <class Model>
+constexpr size_t rng_smem_bytes() { return (size_t)(BLOCK / 32) * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP * sizeof(double); }
+
+template <class Model>
+__device__ __forceinline__ WarpRng<Model::N> make_rng(const EnsembleView &e, int64_t k, bool live)
+{
+	extern __shared__ double jsde_smem[];
+	const int warp = threadIdx.x >> 5;
+	return WarpRng<Model::N>(jsde_smem + warp * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP, e.mt, k - (threadIdx.x & 31), live);
+}
+
 // jitcsde.integrate (_jitcsde.py:597-630) and, with a tape, jitcsde_jump.integrate (:693-700) for every trajectory.
-// Each loop iteration is one attempted step of every lane that still has work; choosing the next target and applying
-// a jump are folded into the same loop so that lanes which jump do not serialise the warp.
+// The warp alternates between (a) cooperative generator refills until every lane that still has work holds the N
+// pairs an attempt may need and (b) one attempted step per such lane.  Choosing the next target and applying a jump
+// are folded into the same loop so that lanes which jump do not serialise the warp.
 template <class Model>
 __global__ void __launch_bounds__(BLOCK) k_integrate(EnsembleView e, Controller c, double target, int use_tape)
 {
+	constexpr int N = Model::N;
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	const bool live = k < e.B;
-	unsigned long long acc = 0, rej = 0, jumps = 0, fresh = 0;
-	int failed_min = 0, failed_ovf = 0, depth = 0;
+	const int64_t kk = live ? k : 0;
+	WarpRng<N> rng = make_rng<Model>(e, k, live);
+	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+	Lane<Model> L(e, kk, rng);
+	unsigned long long acc = 0, rej = 0, jumps = 0;
+	double next_jump = 0.0;
+	bool jump_set = false;
+	long long tape_pos = 0;
+	bool active = false;
 	if (live) {
-		Lane<Model> L(e, k);
 		L.load();
 		if (L.status == TRAJ_MIN_STEP)
 			L.status = TRAJ_OK;  // the reference raises once per call and lets the caller carry on (:569-579)
 		L.cursor = 0;
-		double next_jump = 0.0;
-		bool jump_set = false;
-		long long tape_pos = 0;
 		if (Model::HAS_JUMP && use_tape) {
 			next_jump = e.next_jump[k];
 			jump_set = e.jump_set[k] != 0;
 			tape_pos = e.tape_pos[k];
 		}
-		bool need_target = true, to_jump = false;
-		double tgt = target;
-		while (L.status == TRAJ_OK) {
+		active = L.status == TRAJ_OK;
+	}
+	bool need_target = true, to_jump = false;
+	double tgt = target;
+	while (__any_sync(0xffffffffu, active)) {
+		rng.ensure(active, N);
+		if (active) {
+			bool attempt = true;
 			if (need_target) {
 				tgt = target;
 				to_jump = false;
@@ -90,54 +112,68 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(EnsembleView e, Controller 
 				}
 				need_target = false;
 				if (L.t >= tgt) {  // integrate() with nothing to do (:614)
+					attempt = false;
 					if (!to_jump)
-						break;
-					double change[Model::N];
-					Model::jump(L.t, L.y, e.xis[k * e.tape_len + tape_pos], L.par, change);
+						active = false;
+					else {
+						double change[N];
+						Model::jump(L.t, L.y, e.xis[k * e.tape_len + tape_pos], L.par, change);
 #pragma unroll
-					for (int i = 0; i < Model::N; i++)
-						L.y[i] += change[i];
-					tape_pos++;
-					jumps++;
-					jump_set = false;
-					need_target = true;
-					continue;
+						for (int i = 0; i < N; i++)
+							L.y[i] += change[i];
+						tape_pos++;
+						jumps++;
+						jump_set = false;
+						need_target = true;
+					}
 				}
 			}
-			double actual_dt;
-			bool last;
-			if (L.t + L.dt < tgt) {
-				actual_dt = L.dt;
-				last = false;
-			} else {
-				actual_dt = tgt - L.t;
-				last = true;
-			}
-			if (!L.propose(actual_dt))
-				break;
-			const int verdict = L.adjust_step(c, actual_dt);
-			if (verdict == 1) {
-				L.commit();
-				acc++;
-				if (last) {
-					if (!to_jump)
-						break;
-					double change[Model::N];  // apply_jump(amp(time, state)) (:696-698)
-					Model::jump(L.t, L.y, e.xis[k * e.tape_len + tape_pos], L.par, change);
-#pragma unroll
-					for (int i = 0; i < Model::N; i++)
-						L.y[i] += change[i];
-					tape_pos++;
-					jumps++;
-					jump_set = false;
-					need_target = true;
+			if (attempt) {
+				double actual_dt;
+				bool last;
+				if (L.t + L.dt < tgt) {
+					actual_dt = L.dt;
+					last = false;
+				} else {
+					actual_dt = tgt - L.t;
+					last = true;
 				}
-			} else {
-				rej++;
-				if (verdict < 0)
-					L.status = TRAJ_MIN_STEP;
+				if (!L.propose(actual_dt))
+					active = false;  // noise memory overflow
+				else {
+					const int verdict = L.adjust_step(c, actual_dt);
+					if (verdict == 1) {
+						L.commit();
+						acc++;
+						if (last) {
+							if (!to_jump)
+								active = false;
+							else {
+								double change[N];  // apply_jump(amp(time, state)) (:696-698)
+								Model::jump(L.t, L.y, e.xis[k * e.tape_len + tape_pos], L.par, change);
+#pragma unroll
+								for (int i = 0; i < N; i++)
+									L.y[i] += change[i];
+								tape_pos++;
+								jumps++;
+								jump_set = false;
+								need_target = true;
+							}
+						}
+					} else {
+						rej++;
+						if (verdict < 0) {
+							L.status = TRAJ_MIN_STEP;
+							active = false;
+						}
+					}
+				}
 			}
 		}
+	}
+	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+	int failed_min = 0, failed_ovf = 0;
+	if (live) {
 		L.store();
 		if (Model::HAS_JUMP && use_tape) {
 			e.next_jump[k] = next_jump;
@@ -146,12 +182,10 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(EnsembleView e, Controller 
 		}
 		e.accepted[k] += acc;
 		e.rejected[k] += rej;
-		fresh = L.fresh;
-		depth = L.max_depth;
 		failed_min = L.status == TRAJ_MIN_STEP;
 		failed_ovf = L.status == TRAJ_NOISE_OVERFLOW;
 	}
-	add_totals(e.totals, acc, rej, fresh, jumps, failed_min, failed_ovf, depth);
+	add_totals(e.totals, acc, rej, live ? L.fresh : 0, jumps, failed_min, failed_ovf, live ? L.max_depth : 0);
 }
 
 // ---- single-step surface (reference core methods, one launch each) ---------------------------------------------
@@ -159,15 +193,23 @@ template <class Model>
 __global__ void __launch_bounds__(BLOCK) k_get_next_step(EnsembleView e, const double *h)
 {
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-	if (k >= e.B)
-		return;
-	Lane<Model> L(e, k);
-	L.load();
-	if (L.status == TRAJ_NOISE_OVERFLOW)
-		return;
-	if (L.propose(h[k]))
-		L.store_proposal();
-	L.store();
+	const bool live = k < e.B;
+	const int64_t kk = live ? k : 0;
+	WarpRng<Model::N> rng = make_rng<Model>(e, k, live);
+	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+	Lane<Model> L(e, kk, rng);
+	bool go = false;
+	if (live) {
+		L.load();
+		go = L.status != TRAJ_NOISE_OVERFLOW;
+	}
+	rng.ensure(go, Model::N);
+	if (go) {
+		if (L.propose(h[k]))
+			L.store_proposal();
+		L.store();
+	}
+	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 }
 
 template <class Model>
@@ -176,7 +218,8 @@ __global__ void __launch_bounds__(BLOCK) k_get_p(EnsembleView e, double atol, do
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B)
 		return;
-	Lane<Model> L(e, k);
+	WarpRng<Model::N> rng(nullptr, e.mt, 0, false);
+	Lane<Model> L(e, k, rng);
 	L.load_proposal();
 	p[k] = L.error_ratio(atol, rtol);
 }
@@ -187,7 +230,8 @@ __global__ void __launch_bounds__(BLOCK) k_accept_step(EnsembleView e, const uns
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B || (mask && !mask[k]))
 		return;
-	Lane<Model> L(e, k);
+	WarpRng<Model::N> rng(nullptr, e.mt, 0, false);
+	Lane<Model> L(e, k, rng);
 	L.load();
 	L.load_proposal();
 	L.commit();
@@ -198,14 +242,22 @@ template <class Model>
 __global__ void __launch_bounds__(BLOCK) k_pin_noise(EnsembleView e, unsigned number, double step)
 {
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-	if (k >= e.B)
-		return;
-	Lane<Model> L(e, k);
-	L.load();
-	if (L.status == TRAJ_NOISE_OVERFLOW)
-		return;
-	L.pin(number, step);
-	L.store();
+	const bool live = k < e.B;
+	const int64_t kk = live ? k : 0;
+	WarpRng<Model::N> rng = make_rng<Model>(e, k, live);
+	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+	Lane<Model> L(e, kk, rng);
+	if (live)
+		L.load();
+	for (unsigned j = 0; j < number; j++) {
+		const bool go = live && L.status == TRAJ_OK;
+		rng.ensure(go, Model::N);
+		if (go)
+			L.pin_one(step);
+	}
+	if (live)
+		L.store();
+	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 }
 
 // rk_gauss stream of every trajectory: out [B][pairs][2]
@@ -213,19 +265,21 @@ template <class Model>
 __global__ void __launch_bounds__(BLOCK) k_draw_gauss(EnsembleView e, double scale, int pairs, double *out)
 {
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-	if (k >= e.B)
-		return;
-	Lane<Model> L(e, k);
-	L.load();
+	const bool live = k < e.B;
+	const int64_t kk = live ? k : 0;
+	WarpRng<Model::N> rng = make_rng<Model>(e, k, live);
+	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 	for (int j = 0; j < pairs; j++) {
-		double x1, x2, r2;
-		while (!polar_candidate(L.next_words(), x1, x2, r2)) {
+		rng.ensure(live, 1);
+		if (live) {
+			double x1, x2, r2;
+			rng.pop(x1, x2, r2);
+			const double f = scale * polar_radius_factor(r2);
+			out[(k * pairs + j) * 2] = x1 * f;
+			out[(k * pairs + j) * 2 + 1] = x2 * f;
 		}
-		const double f = scale * polar_radius_factor(r2);
-		out[(k * pairs + j) * 2] = x1 * f;
-		out[(k * pairs + j) * 2 + 1] = x2 * f;
 	}
-	L.store();
+	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 }
 
 // ---- model-independent helpers ------------------------------------------------------------------------------------

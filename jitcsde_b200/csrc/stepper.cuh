@@ -13,8 +13,7 @@
 #pragma once
 
 #include "ensemble.cuh"
-#include "gauss.cuh"
-#include "mt19937.cuh"
+#include "warp_rng.cuh"
 
 namespace jsde {
 
@@ -28,17 +27,17 @@ struct Lane {
 
 	const EnsembleView &e;
 	const int64_t k;
-	uint4 *S;
+	WarpRng<N> &rng;
 
 	double y[N], t, dt;
 	double ny[N], er[N], nt;  // last proposal
 	double par[NP > 0 ? NP : 1];
-	int count, cursor, chunk, status;
+	int count, cursor, status;
 	unsigned fresh;
 	int max_depth;
 
-	__device__ __forceinline__ Lane(const EnsembleView &view, int64_t index)
-		: e(view), k(index), S(view.mt + index * MT_CHUNKS), fresh(0), max_depth(0) {}
+	__device__ __forceinline__ Lane(const EnsembleView &view, int64_t index, WarpRng<N> &source)
+		: e(view), k(index), rng(source), fresh(0), max_depth(0) {}
 
 	// ---- global-memory accessors ---------------------------------------------------------------------------
 	__device__ __forceinline__ double &qh(int d) const { return e.q_h[(int64_t)d * e.B + k]; }
@@ -53,7 +52,6 @@ struct Lane {
 		dt = e.dt[k];
 		count = e.q_count[k];
 		cursor = e.q_cursor[k];
-		chunk = e.mt_chunk[k];
 		status = e.status[k];
 #pragma unroll
 		for (int i = 0; i < NP; i++)
@@ -69,7 +67,6 @@ struct Lane {
 		e.dt[k] = dt;
 		e.q_count[k] = count;
 		e.q_cursor[k] = cursor;
-		e.mt_chunk[k] = chunk;
 		e.status[k] = status;
 	}
 
@@ -94,43 +91,18 @@ struct Lane {
 	}
 
 	// ---- generator ---------------------------------------------------------------------------------------------
-	__device__ __forceinline__ uint4 next_words()
-	{
-		uint4 w = mt_consume_chunk(S, chunk);
-		chunk = mt_wrap(chunk + 1);
-		w.x = mt_temper(w.x);
-		w.y = mt_temper(w.y);
-		w.z = mt_temper(w.z);
-		w.w = mt_temper(w.w);
-		return w;
-	}
-
-	// get_gauss (template:145-154): components in order, one accepted pair each.  The per-component rejection loops
-	// are flattened into one loop with a per-lane component cursor, so a warp iterates max-over-lanes of the *total*
-	// number of candidates instead of the sum of per-component maxima; log/div/sqrt run after it, convergent.
+	// get_gauss (template:145-154): components in order, one accepted pair each, popped from this lane's FIFO (the
+	// caller has run rng.ensure(…, N) with the whole warp).  Only the scale-dependent tail of rk_gauss is left:
+	// f = scale*sqrt(-2*log(r2)/r2), DW = x1*f, DZ = x2*f (random_numbers.c:127-129).
 	__device__ __forceinline__ void draw(double scale, double (&gW)[N], double (&gZ)[N])
 	{
-		double r2s[N];
-		int c = 0;
-		while (c < N) {
-			double x1, x2, r2;
-			const bool ok = polar_candidate(next_words(), x1, x2, r2);
-			if (ok) {
-#pragma unroll
-				for (int i = 0; i < N; i++)
-					if (i == c) {
-						gW[i] = x1;
-						gZ[i] = x2;
-						r2s[i] = r2;
-					}
-				c++;
-			}
-		}
 #pragma unroll
 		for (int i = 0; i < N; i++) {
-			const double f = scale * polar_radius_factor(r2s[i]);
-			gW[i] *= f;
-			gZ[i] *= f;
+			double x1, x2, r2;
+			rng.pop(x1, x2, r2);
+			const double f = scale * polar_radius_factor(r2);
+			gW[i] = x1 * f;
+			gZ[i] = x2 * f;
 		}
 	}
 
@@ -230,26 +202,24 @@ struct Lane {
 		return true;
 	}
 
-	// pin_noise (template:252-267): append `number` fresh items of length `step`
-	__device__ __forceinline__ void pin(unsigned number, double step)
+	// pin_noise (template:252-267): append one fresh item of length `step` (the kernel loops `number` times so that the
+	// whole warp can refill its generator FIFOs between items)
+	__device__ __forceinline__ void pin_one(double step)
 	{
-		for (unsigned j = 0; j < number; j++) {
-			if (count >= e.D) {
-				status = TRAJ_NOISE_OVERFLOW;
-				return;
-			}
-			double gW[N], gZ[N];
-			draw(sqrt(step), gW, gZ);
-			qh(count) = step;
-#pragma unroll
-			for (int i = 0; i < N; i++) {
-				qw(count, i) = gW[i];
-				qw(count, N + i) = gZ[i];
-			}
-			count++;
+		if (count >= e.D) {
+			status = TRAJ_NOISE_OVERFLOW;
+			return;
 		}
-		if (number)
-			cursor = count - 1;  // template:173: current_noise = the newest item, so an accept_step right after keeps only it
+		double gW[N], gZ[N];
+		draw(sqrt(step), gW, gZ);
+		qh(count) = step;
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			qw(count, i) = gW[i];
+			qw(count, N + i) = gZ[i];
+		}
+		count++;
+		cursor = count - 1;  // template:173: current_noise = the newest item, so an accept_step right after keeps only it
 		max_depth = count > max_depth ? count : max_depth;
 	}
 

@@ -37,6 +37,18 @@ FLAGS = {
 }
 
 
+def cpu_signature() -> str:
+	"""Digest of the host CPU's feature flags: a -march=native build is only valid on a CPU with the same features."""
+	import hashlib
+	try:
+		for line in open("/proc/cpuinfo"):
+			if line.startswith("flags"):
+				return hashlib.sha256(" ".join(sorted(line.split(":", 1)[1].split())).encode()).hexdigest()[:12]
+	except OSError:
+		pass
+	return "unknown"
+
+
 def module_name(spec, flavour: str) -> str:
 	return f"jsderef_{spec.name}_{flavour}"
 
@@ -101,6 +113,8 @@ def build(spec, flavour: str = "strict", force: bool = False) -> str:
 			raise RuntimeError("reference core failed to compile:\n" + res.stderr[-4000:])
 	with open(stamp, "w") as fh:
 		fh.write(spec.digest())
+	with open(target + ".cpu", "w") as fh:
+		fh.write(cpu_signature())
 	return target
 
 
@@ -123,4 +137,14 @@ def load(spec, flavour: str = "strict"):
 
 
 def available(spec, flavour: str = "strict") -> bool:
-	return reference_available() or os.path.isfile(os.path.join(OUT_DIR, module_name(spec, flavour) + ".so"))
+	if reference_available():
+		return True
+	target = os.path.join(OUT_DIR, module_name(spec, flavour) + ".so")
+	if not os.path.isfile(target):
+		return False
+	if flavour == "default":  # built with -march=native: usable only on a CPU with the same feature set
+		try:
+			return open(target + ".cpu").read() == cpu_signature()
+		except OSError:
+			return False
+	return True
