@@ -40,32 +40,41 @@ static inline double jsde_asd_(uint64_t u) { double x; memcpy(&x, &u, 8); return
 #include "glibc_tables.h"
 
 // ---- log --------------------------------------------------------------------------------------------------
-JSDE_FN double jsde_log(double x)
+// glibc splits on |x-1|: inputs in [1-2^-4, 1+0x1.09p-4) take a table-free polynomial, everything else the table
+// path.  The two halves are exposed separately so that a SIMT caller can run the (long, rare: 6 % of polar radii)
+// near-one half only for the lanes and components that need it.
+JSDE_FN int jsde_log_is_near_one(double x)
 {
-	const uint64_t ix = JSDE_ASU(x);
 	const uint64_t LO = 0x3fee000000000000ULL;  // asuint64(1 - 0x1p-4)
 	const uint64_t HI = 0x3ff1090000000000ULL;  // asuint64(1 + 0x1.09p-4)
-	if (ix - LO < HI - LO) {
-		// |x-1| small: direct polynomial, no table (avoids cancellation)
-		if (ix == 0x3ff0000000000000ULL) return 0.0;
-		const double r = x - 1.0;
-		const double r2 = r * r;
-		const double r3 = r * r2;
-		const double P1 = JSDE_FMA(r2, JSDE_LOG_B3, JSDE_FMA(r, JSDE_LOG_B2, JSDE_LOG_B1));
-		const double P2 = JSDE_FMA(r2, JSDE_LOG_B6, JSDE_FMA(r, JSDE_LOG_B5, JSDE_LOG_B4));
-		const double P3 = JSDE_FMA(r3, JSDE_LOG_B10, JSDE_FMA(r2, JSDE_LOG_B9, JSDE_FMA(r, JSDE_LOG_B8, JSDE_LOG_B7)));
-		const double Q = JSDE_FMA(JSDE_FMA(P3, r3, P2), r3, P1);
-		// split r into rhi + rlo so that rhi*rhi*B0 is exact enough
-		const double w = JSDE_FMA(r, 0x1p27, r);
-		const double rhi = JSDE_FMA(-0x1p27, r, w);
-		const double rlo = r - rhi;
-		const double s = rhi * rhi;
-		const double hi = JSDE_FMA(s, JSDE_LOG_B0, r);
-		const double lo = JSDE_FMA(s, JSDE_LOG_B0, r - hi);
-		const double lo2 = JSDE_FMA(JSDE_LOG_B0 * rlo, rhi + r, lo);
-		return JSDE_FMA(Q, r3, lo2) + hi;
-	}
-	// x = 2^k z, z in [0x1.69555p-1, 0x1.69555p0); table on the top 7 mantissa bits of z
+	return JSDE_ASU(x) - LO < HI - LO;
+}
+
+JSDE_FN double jsde_log_near_one(double x)
+{
+	if (JSDE_ASU(x) == 0x3ff0000000000000ULL) return 0.0;
+	const double r = x - 1.0;
+	const double r2 = r * r;
+	const double r3 = r * r2;
+	const double P1 = JSDE_FMA(r2, JSDE_LOG_B3, JSDE_FMA(r, JSDE_LOG_B2, JSDE_LOG_B1));
+	const double P2 = JSDE_FMA(r2, JSDE_LOG_B6, JSDE_FMA(r, JSDE_LOG_B5, JSDE_LOG_B4));
+	const double P3 = JSDE_FMA(r3, JSDE_LOG_B10, JSDE_FMA(r2, JSDE_LOG_B9, JSDE_FMA(r, JSDE_LOG_B8, JSDE_LOG_B7)));
+	const double Q = JSDE_FMA(JSDE_FMA(P3, r3, P2), r3, P1);
+	// split r into rhi + rlo so that rhi*rhi*B0 is exact enough
+	const double w = JSDE_FMA(r, 0x1p27, r);
+	const double rhi = JSDE_FMA(-0x1p27, r, w);
+	const double rlo = r - rhi;
+	const double s = rhi * rhi;
+	const double hi = JSDE_FMA(s, JSDE_LOG_B0, r);
+	const double lo = JSDE_FMA(s, JSDE_LOG_B0, r - hi);
+	const double lo2 = JSDE_FMA(JSDE_LOG_B0 * rlo, rhi + r, lo);
+	return JSDE_FMA(Q, r3, lo2) + hi;
+}
+
+// x = 2^k z, z in [0x1.69555p-1, 0x1.69555p0); table on the top 7 mantissa bits of z
+JSDE_FN double jsde_log_table(double x)
+{
+	const uint64_t ix = JSDE_ASU(x);
 	const uint64_t tmp = ix - 0x3fe6000000000000ULL;
 	const int i = (int)((tmp >> 45) & 127);
 	const int64_t k = (int64_t)tmp >> 52;
@@ -82,6 +91,11 @@ JSDE_FN double jsde_log(double x)
 	const double r3 = r * r2;
 	const double q = JSDE_FMA(JSDE_FMA(r, JSDE_LOG_A4, JSDE_LOG_A3), r2, JSDE_FMA(r, JSDE_LOG_A2, JSDE_LOG_A1));
 	return JSDE_FMA(r3, q, JSDE_FMA(r2, JSDE_LOG_A0, lo)) + hi;
+}
+
+JSDE_FN double jsde_log(double x)
+{
+	return jsde_log_is_near_one(x) ? jsde_log_near_one(x) : jsde_log_table(x);
 }
 
 // ---- pow --------------------------------------------------------------------------------------------------

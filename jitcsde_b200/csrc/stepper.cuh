@@ -28,6 +28,7 @@ struct Lane {
 	const EnsembleView &e;
 	const int64_t k;
 	WarpRng<N> &rng;
+	double *const qh0, *const qw0;  // this trajectory's column of the noise-memory arrays
 
 	double y[N], t, dt;
 	double ny[N], er[N], nt;  // last proposal
@@ -37,11 +38,11 @@ struct Lane {
 	int max_depth;
 
 	__device__ __forceinline__ Lane(const EnsembleView &view, int64_t index, WarpRng<N> &source)
-		: e(view), k(index), rng(source), fresh(0), max_depth(0) {}
+		: e(view), k(index), rng(source), qh0(view.q_h + index), qw0(view.q_w + index), fresh(0), max_depth(0) {}
 
 	// ---- global-memory accessors ---------------------------------------------------------------------------
-	__device__ __forceinline__ double &qh(int d) const { return e.q_h[(int64_t)d * e.B + k]; }
-	__device__ __forceinline__ double &qw(int d, int c) const { return e.q_w[((int64_t)d * (2 * N) + c) * e.B + k]; }
+	__device__ __forceinline__ double &qh(int d) const { return qh0[(int64_t)d * e.B]; }
+	__device__ __forceinline__ double &qw(int d, int c) const { return qw0[(int64_t)(d * (2 * N) + c) * e.B]; }
 
 	__device__ __forceinline__ void load()
 	{
@@ -96,13 +97,35 @@ struct Lane {
 	// f = scale*sqrt(-2*log(r2)/r2), DW = x1*f, DZ = x2*f (random_numbers.c:127-129).
 	__device__ __forceinline__ void draw(double scale, double (&gW)[N], double (&gZ)[N])
 	{
+		double r2[N], lg[N];
+		unsigned pending = 0;  // components whose radius needs glibc's near-one log branch
 #pragma unroll
 		for (int i = 0; i < N; i++) {
-			double x1, x2, r2;
-			rng.pop(x1, x2, r2);
-			const double f = scale * polar_radius_factor(r2);
-			gW[i] = x1 * f;
-			gZ[i] = x2 * f;
+			rng.pop(gW[i], gZ[i], r2[i]);
+			lg[i] = jsde_log_table(r2[i]);  // convergent; overwritten below for the ~6 % near-one radii
+			if (jsde_log_is_near_one(r2[i]))
+				pending |= 1u << i;
+		}
+		// the long near-one branch runs once per lane-with-such-a-component, not once per component for the whole warp
+		while (pending) {
+			const int which = __ffs(pending) - 1;
+			pending &= pending - 1;
+			double x = r2[0];
+#pragma unroll
+			for (int i = 1; i < N; i++)
+				if (i == which)
+					x = r2[i];
+			const double v = jsde_log_near_one(x);
+#pragma unroll
+			for (int i = 0; i < N; i++)
+				if (i == which)
+					lg[i] = v;
+		}
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			const double f = scale * sqrt(__ddiv_rn(__dmul_rn(-2.0, lg[i]), r2[i]));
+			gW[i] *= f;
+			gZ[i] *= f;
 		}
 	}
 
@@ -334,14 +357,19 @@ struct Lane {
 	__device__ __forceinline__ int adjust_step(const Controller &c, double actual_dt)
 	{
 		const double p = error_ratio(c.atol, c.rtol);
-		if (p > c.dec_thr) {
-			const double pw = (p > 1.7976931348623157e308) ? 0.0 : jsde_pow(p, c.shrink_exp);  // inf ** negative = 0.0
+		const bool rejecting = p > c.dec_thr;
+		const bool growing = !rejecting && p <= c.inc_thr;
+		// one call site for both uses of Python's `**` (:587, :592) so that rejecting and growing lanes share it
+		double pw = 0.0;  // inf ** negative = 0.0
+		if ((rejecting && p <= 1.7976931348623157e308) || (growing && p != 0.0))
+			pw = jsde_pow(p, rejecting ? c.shrink_exp : c.grow_exp);
+		if (rejecting) {
 			const double shrink = c.safety * pw;
 			dt = actual_dt * (c.min_factor > shrink ? c.min_factor : shrink);
 			return dt < c.min_step ? -1 : 0;
 		}
-		if (p <= c.inc_thr) {
-			const double factor = (p != 0.0) ? c.safety * jsde_pow(p, c.grow_exp) : c.max_factor;
+		if (growing) {
+			const double factor = (p != 0.0) ? c.safety * pw : c.max_factor;
 			const double sug = actual_dt * (c.max_factor < factor ? c.max_factor : factor);
 			const double capped = c.max_step < sug ? c.max_step : sug;
 			dt = capped > dt ? capped : dt;

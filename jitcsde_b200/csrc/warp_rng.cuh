@@ -74,61 +74,97 @@ struct WarpRng {
 		}
 	}
 
-	// ---- one cooperative refill step; `want` = lanes whose FIFO has room for a full group (first four are served) ----
-	__device__ __forceinline__ void refill_op(unsigned want)
+	// ---- cooperative refill: K slots of (4 trajectories x 8 candidates) with all global loads issued up front ----------
+	// `room` = lanes whose FIFO can take a full group; the first 4K of them (lane order) are served, each exactly once.
+	template <int K>
+	__device__ __forceinline__ void refill(unsigned room)
 	{
 		const unsigned full = 0xffffffffu;
 		const int g = lane >> 3, j = lane & 7;
-		const unsigned T = __fns(want, 0, g + 1);  // g-th set bit, 0xffffffff if there is none
-		const bool have = T < 32u;
-		const int Ts = have ? (int)T : 0;
-		const int cT = __shfl_sync(full, chunk, Ts);
-		const int rdT = __shfl_sync(full, rd, Ts);
-		const int lvT = __shfl_sync(full, lvl, Ts);
-		uint4 *ST = S0 + (int64_t)Ts * MT_CHUNKS;
-		const int c = mt_wrap(cT + j);
-		uint4 a = make_uint4(0, 0, 0, 0), tap = make_uint4(0, 0, 0, 0);
-		if (have) {
-			a = ST[c];
-			tap = ST[mt_wrap(c + 99)];
+		// rank-(4s+g) set bit of `room` for slot s: strip g lowest bits once, then 4 more per slot
+		unsigned m = room;
+		if (g >= 1) m &= m - 1;
+		if (g >= 2) m &= m - 1;
+		if (g >= 3) m &= m - 1;
+		int Ts[K], c[K];
+		bool have[K];
+		uint4 a[K], tap[K];
+		uint4 *ST[K];
+#pragma unroll
+		for (int s = 0; s < K; s++) {
+			have[s] = m != 0;
+			Ts[s] = have[s] ? __ffs(m) - 1 : 0;
+			m &= m - 1; m &= m - 1; m &= m - 1; m &= m - 1;
+			ST[s] = S0 + (int64_t)Ts[s] * MT_CHUNKS;
+			c[s] = mt_wrap(__shfl_sync(full, chunk, Ts[s]) + j);
+			a[s] = make_uint4(0, 0, 0, 0);
+			tap[s] = make_uint4(0, 0, 0, 0);
 		}
-		uint32_t next = __shfl_down_sync(full, a.x, 1);
-		uint32_t tap_hi = __shfl_down_sync(full, tap.x, 1);
-		if (have && j == RNG_GROUP - 1) {
-			next = reinterpret_cast<const uint32_t *>(ST + mt_wrap(c + 1))[0];
-			tap_hi = reinterpret_cast<const uint32_t *>(ST + mt_wrap(c + 100))[0];
+#pragma unroll
+		for (int s = 0; s < K; s++)
+			if (have[s]) {
+				a[s] = ST[s][c[s]];
+				tap[s] = ST[s][mt_wrap(c[s] + 99)];
+			}
+		uint32_t edge_next[K], edge_tap[K];
+#pragma unroll
+		for (int s = 0; s < K; s++) {
+			edge_next[s] = 0;
+			edge_tap[s] = 0;
+			if (have[s] && j == RNG_GROUP - 1) {
+				edge_next[s] = reinterpret_cast<const uint32_t *>(ST[s] + mt_wrap(c[s] + 1))[0];
+				edge_tap[s] = reinterpret_cast<const uint32_t *>(ST[s] + mt_wrap(c[s] + 100))[0];
+			}
 		}
-		bool ok = false;
-		double x1 = 0.0, x2 = 0.0, r2 = 0.0;
-		if (have) {
-			uint4 r;
-			r.x = tap.y ^ mt_mix(a.x, a.y);
-			r.y = tap.z ^ mt_mix(a.y, a.z);
-			r.z = tap.w ^ mt_mix(a.z, a.w);
-			r.w = tap_hi ^ mt_mix(a.w, next);
-			ST[c] = r;
-			a.x = mt_temper(a.x);
-			a.y = mt_temper(a.y);
-			a.z = mt_temper(a.z);
-			a.w = mt_temper(a.w);
-			ok = polar_candidate(a, x1, x2, r2);
+		int cnt[K];
+#pragma unroll
+		for (int s = 0; s < K; s++) {
+			const int rdT = __shfl_sync(full, rd, Ts[s]);
+			const int lvT = __shfl_sync(full, lvl, Ts[s]);
+			uint32_t next = __shfl_down_sync(full, a[s].x, 1);
+			uint32_t tap_hi = __shfl_down_sync(full, tap[s].x, 1);
+			if (j == RNG_GROUP - 1) {
+				next = edge_next[s];
+				tap_hi = edge_tap[s];
+			}
+			bool ok = false;
+			double x1 = 0.0, x2 = 0.0, r2 = 0.0;
+			if (have[s]) {
+				uint4 r;
+				r.x = tap[s].y ^ mt_mix(a[s].x, a[s].y);
+				r.y = tap[s].z ^ mt_mix(a[s].y, a[s].z);
+				r.z = tap[s].w ^ mt_mix(a[s].z, a[s].w);
+				r.w = tap_hi ^ mt_mix(a[s].w, next);
+				ST[s][c[s]] = r;
+				uint4 w;
+				w.x = mt_temper(a[s].x);
+				w.y = mt_temper(a[s].y);
+				w.z = mt_temper(a[s].z);
+				w.w = mt_temper(a[s].w);
+				ok = polar_candidate(w, x1, x2, r2);
+			}
+			const unsigned okm = __ballot_sync(full, ok);
+			const unsigned grp = (okm >> (g * RNG_GROUP)) & 0xffu;
+			const int rank = __popc(grp & ((1u << j) - 1u));
+			cnt[s] = __popc(grp);
+			if (ok) {
+				int slot = rdT + lvT + rank;
+				slot = slot >= CAP ? slot - CAP : slot;
+				fx1[slot * RNG_STRIDE + Ts[s]] = x1;
+				fx2[slot * RNG_STRIDE + Ts[s]] = x2;
+				fr2[slot * RNG_STRIDE + Ts[s]] = r2;
+			}
 		}
-		const unsigned okm = __ballot_sync(full, ok);
-		const unsigned grp = (okm >> (g * RNG_GROUP)) & 0xffu;
-		const int rank = __popc(grp & ((1u << j) - 1u));
-		const int cnt = __popc(grp);
-		if (ok) {
-			int s = rdT + lvT + rank;
-			s = s >= CAP ? s - CAP : s;
-			s = s >= CAP ? s - CAP : s;
-			fx1[s * RNG_STRIDE + Ts] = x1;
-			fx2[s * RNG_STRIDE + Ts] = x2;
-			fr2[s * RNG_STRIDE + Ts] = r2;
+		// owners: the lane whose trajectory has rank r among `room` was served by slot r/4, group r%4
+		const int below = __popc(room & ((1u << lane) - 1u));
+		const bool served = ((room >> lane) & 1u) && below < 4 * K;
+		int mine = 0;
+#pragma unroll
+		for (int s = 0; s < K; s++) {
+			const int v = __shfl_sync(full, cnt[s], (below & 3) * RNG_GROUP);
+			if ((below >> 2) == s)
+				mine = v;
 		}
-		// owners: the lane whose trajectory was the i-th one served learns its group's count from lane 8*i
-		const int below = __popc(want & ((1u << lane) - 1u));
-		const bool served = ((want >> lane) & 1u) && below < 32 / RNG_GROUP;
-		const int mine = __shfl_sync(full, cnt, (below & 3) * RNG_GROUP);
 		if (served) {
 			lvl += mine;
 			chunk = mt_wrap(chunk + RNG_GROUP);
@@ -137,13 +173,21 @@ struct WarpRng {
 	}
 
 	// Make sure every lane with `wants` holds at least `need` pairs.  Whole warp must call (convergent).
+	// Everybody with room is served, not only the needy: every slot does useful work as long as it is full.
 	__device__ __forceinline__ void ensure(bool wants, int need)
 	{
 		const unsigned full = 0xffffffffu;
 		while (__ballot_sync(full, wants && usable && lvl < need)) {
-			// serve whoever has room: every op does useful work as long as it is full; needy lanes always have room
 			const unsigned room = __ballot_sync(full, wants && usable && lvl <= CAP - RNG_GROUP);
-			refill_op(room);
+			const int n = __popc(room);
+			if (n > 12)
+				refill<4>(room);
+			else if (n > 8)
+				refill<3>(room);
+			else if (n > 4)
+				refill<2>(room);
+			else
+				refill<1>(room);
 		}
 	}
 
