@@ -176,8 +176,10 @@ struct Lane {
 			draw(scale, gW, gZ);
 			fresh++;
 			if (bridging) {
+#pragma unroll 1
 				for (int d = count - 1; d > cur; d--) {  // make room behind the cursor (the reference relinks its list)
 					qh(d + 1) = qh(d);
+#pragma unroll 1
 					for (int c = 0; c < 2 * N; c++)
 						qw(d + 1, c) = qw(d, c);
 				}
@@ -342,12 +344,15 @@ struct Lane {
 			y[i] = ny[i];
 		t = nt;
 		const int rest = count - cursor;
-		if (cursor > 0)
+		if (cursor > 0) {
+#pragma unroll 1
 			for (int d = 0; d < rest; d++) {
 				qh(d) = qh(d + cursor);
+#pragma unroll 1
 				for (int c = 0; c < 2 * N; c++)
 					qw(d, c) = qw(d + cursor, c);
 			}
+		}
 		count = rest;
 		cursor = 0;
 	}

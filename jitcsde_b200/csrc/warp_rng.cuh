@@ -25,10 +25,12 @@ namespace jsde {
 constexpr int RNG_GROUP = 8;     // candidates per trajectory per op
 constexpr int RNG_STRIDE = 33;   // row stride (doubles) of the FIFO arrays: conflict-free column writes
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int N>
 struct WarpRng {
-	// room for the pairs left over below one draw's need (N-1) plus a full group, rounded up
-	static constexpr int CAP = ((N - 1 + RNG_GROUP + 3) / 4) * 4;
+	// room for the pairs left over below one draw's need (N-1) plus a full group
+	static constexpr int CAP = N - 1 + RNG_GROUP;
 	static constexpr int SMEM_DOUBLES_PER_WARP = 3 * CAP * RNG_STRIDE;
 
 	double *fx1, *fx2, *fr2;  // this warp's FIFO arrays [CAP][RNG_STRIDE]
@@ -74,98 +76,100 @@ struct WarpRng {
 		}
 	}
 
-	// ---- cooperative refill: K slots of (4 trajectories x 8 candidates) with all global loads issued up front ----------
-	// `room` = lanes whose FIFO can take a full group; the first 4K of them (lane order) are served, each exactly once.
-	template <int K>
+	// ---- cooperative refill ------------------------------------------------------------------------------------------
+	// `room` = lanes whose FIFO can take a full group.  They are served four at a time ("slot": 4 trajectories x 8
+	// candidates), each exactly once.  Pass 1 only prefetches every slot's state lines into L1 so that the memory
+	// latency is paid once per refill, not once per slot; pass 2 does the work.  Both are run-time loops: unrolling
+	// them blew the 32 KB instruction cache (profiles/r01_v3_*: 40 % of stall samples were instruction fetch).
 	__device__ __forceinline__ void refill(unsigned room)
 	{
 		const unsigned full = 0xffffffffu;
 		const int g = lane >> 3, j = lane & 7;
+		const int slots = (__popc(room) + 3) >> 2;
 		// rank-(4s+g) set bit of `room` for slot s: strip g lowest bits once, then 4 more per slot
-		unsigned m = room;
-		if (g >= 1) m &= m - 1;
-		if (g >= 2) m &= m - 1;
-		if (g >= 3) m &= m - 1;
-		int Ts[K], c[K];
-		bool have[K];
-		uint4 a[K], tap[K];
-		uint4 *ST[K];
-#pragma unroll
-		for (int s = 0; s < K; s++) {
-			have[s] = m != 0;
-			Ts[s] = have[s] ? __ffs(m) - 1 : 0;
+		unsigned m0 = room;
+		if (g >= 1) m0 &= m0 - 1;
+		if (g >= 2) m0 &= m0 - 1;
+		if (g >= 3) m0 &= m0 - 1;
+		if (slots > 1) {
+			unsigned m = m0;
+#pragma unroll 1
+			for (int s = 0; s < slots; s++) {
+				const bool have = m != 0;
+				const int T = have ? __ffs(m) - 1 : 0;
+				m &= m - 1; m &= m - 1; m &= m - 1; m &= m - 1;
+				const int c = mt_wrap(__shfl_sync(full, chunk, T) + j);
+				if (have) {
+					const uint4 *ST = S0 + (int64_t)T * MT_CHUNKS;
+					prefetch_l1(ST + c);
+					prefetch_l1(ST + mt_wrap(c + 99));
+					if (j == RNG_GROUP - 1) {
+						prefetch_l1(ST + mt_wrap(c + 1));
+						prefetch_l1(ST + mt_wrap(c + 100));
+					}
+				}
+			}
+		}
+		const int below = __popc(room & ((1u << lane) - 1u));
+		int mine = 0;
+		unsigned m = m0;
+#pragma unroll 1
+		for (int s = 0; s < slots; s++) {
+			const bool have = m != 0;
+			const int T = have ? __ffs(m) - 1 : 0;
 			m &= m - 1; m &= m - 1; m &= m - 1; m &= m - 1;
-			ST[s] = S0 + (int64_t)Ts[s] * MT_CHUNKS;
-			c[s] = mt_wrap(__shfl_sync(full, chunk, Ts[s]) + j);
-			a[s] = make_uint4(0, 0, 0, 0);
-			tap[s] = make_uint4(0, 0, 0, 0);
-		}
-#pragma unroll
-		for (int s = 0; s < K; s++)
-			if (have[s]) {
-				a[s] = ST[s][c[s]];
-				tap[s] = ST[s][mt_wrap(c[s] + 99)];
+			uint4 *ST = S0 + (int64_t)T * MT_CHUNKS;
+			const int c = mt_wrap(__shfl_sync(full, chunk, T) + j);
+			const int rdT = __shfl_sync(full, rd, T);
+			const int lvT = __shfl_sync(full, lvl, T);
+			uint4 a = make_uint4(0, 0, 0, 0), tap = make_uint4(0, 0, 0, 0);
+			uint32_t edge_next = 0, edge_tap = 0;
+			if (have) {
+				a = ST[c];
+				tap = ST[mt_wrap(c + 99)];
+				if (j == RNG_GROUP - 1) {
+					edge_next = reinterpret_cast<const uint32_t *>(ST + mt_wrap(c + 1))[0];
+					edge_tap = reinterpret_cast<const uint32_t *>(ST + mt_wrap(c + 100))[0];
+				}
 			}
-		uint32_t edge_next[K], edge_tap[K];
-#pragma unroll
-		for (int s = 0; s < K; s++) {
-			edge_next[s] = 0;
-			edge_tap[s] = 0;
-			if (have[s] && j == RNG_GROUP - 1) {
-				edge_next[s] = reinterpret_cast<const uint32_t *>(ST[s] + mt_wrap(c[s] + 1))[0];
-				edge_tap[s] = reinterpret_cast<const uint32_t *>(ST[s] + mt_wrap(c[s] + 100))[0];
-			}
-		}
-		int cnt[K];
-#pragma unroll
-		for (int s = 0; s < K; s++) {
-			const int rdT = __shfl_sync(full, rd, Ts[s]);
-			const int lvT = __shfl_sync(full, lvl, Ts[s]);
-			uint32_t next = __shfl_down_sync(full, a[s].x, 1);
-			uint32_t tap_hi = __shfl_down_sync(full, tap[s].x, 1);
+			uint32_t next = __shfl_down_sync(full, a.x, 1);
+			uint32_t tap_hi = __shfl_down_sync(full, tap.x, 1);
 			if (j == RNG_GROUP - 1) {
-				next = edge_next[s];
-				tap_hi = edge_tap[s];
+				next = edge_next;
+				tap_hi = edge_tap;
 			}
 			bool ok = false;
 			double x1 = 0.0, x2 = 0.0, r2 = 0.0;
-			if (have[s]) {
+			if (have) {
 				uint4 r;
-				r.x = tap[s].y ^ mt_mix(a[s].x, a[s].y);
-				r.y = tap[s].z ^ mt_mix(a[s].y, a[s].z);
-				r.z = tap[s].w ^ mt_mix(a[s].z, a[s].w);
-				r.w = tap_hi ^ mt_mix(a[s].w, next);
-				ST[s][c[s]] = r;
-				uint4 w;
-				w.x = mt_temper(a[s].x);
-				w.y = mt_temper(a[s].y);
-				w.z = mt_temper(a[s].z);
-				w.w = mt_temper(a[s].w);
-				ok = polar_candidate(w, x1, x2, r2);
+				r.x = tap.y ^ mt_mix(a.x, a.y);
+				r.y = tap.z ^ mt_mix(a.y, a.z);
+				r.z = tap.w ^ mt_mix(a.z, a.w);
+				r.w = tap_hi ^ mt_mix(a.w, next);
+				ST[c] = r;
+				a.x = mt_temper(a.x);
+				a.y = mt_temper(a.y);
+				a.z = mt_temper(a.z);
+				a.w = mt_temper(a.w);
+				ok = polar_candidate(a, x1, x2, r2);
 			}
 			const unsigned okm = __ballot_sync(full, ok);
 			const unsigned grp = (okm >> (g * RNG_GROUP)) & 0xffu;
 			const int rank = __popc(grp & ((1u << j) - 1u));
-			cnt[s] = __popc(grp);
+			const int cnt = __popc(grp);
 			if (ok) {
 				int slot = rdT + lvT + rank;
 				slot = slot >= CAP ? slot - CAP : slot;
-				fx1[slot * RNG_STRIDE + Ts[s]] = x1;
-				fx2[slot * RNG_STRIDE + Ts[s]] = x2;
-				fr2[slot * RNG_STRIDE + Ts[s]] = r2;
+				fx1[slot * RNG_STRIDE + T] = x1;
+				fx2[slot * RNG_STRIDE + T] = x2;
+				fr2[slot * RNG_STRIDE + T] = r2;
 			}
-		}
-		// owners: the lane whose trajectory has rank r among `room` was served by slot r/4, group r%4
-		const int below = __popc(room & ((1u << lane) - 1u));
-		const bool served = ((room >> lane) & 1u) && below < 4 * K;
-		int mine = 0;
-#pragma unroll
-		for (int s = 0; s < K; s++) {
-			const int v = __shfl_sync(full, cnt[s], (below & 3) * RNG_GROUP);
+			// owner: the lane whose trajectory has rank r among `room` is served by slot r/4, group r%4
+			const int v = __shfl_sync(full, cnt, (below & 3) * RNG_GROUP);
 			if ((below >> 2) == s)
 				mine = v;
 		}
-		if (served) {
+		if ((room >> lane) & 1u) {
 			lvl += mine;
 			chunk = mt_wrap(chunk + RNG_GROUP);
 		}
@@ -177,18 +181,8 @@ struct WarpRng {
 	__device__ __forceinline__ void ensure(bool wants, int need)
 	{
 		const unsigned full = 0xffffffffu;
-		while (__ballot_sync(full, wants && usable && lvl < need)) {
-			const unsigned room = __ballot_sync(full, wants && usable && lvl <= CAP - RNG_GROUP);
-			const int n = __popc(room);
-			if (n > 12)
-				refill<4>(room);
-			else if (n > 8)
-				refill<3>(room);
-			else if (n > 4)
-				refill<2>(room);
-			else
-				refill<1>(room);
-		}
+		while (__ballot_sync(full, wants && usable && lvl < need))
+			refill(__ballot_sync(full, wants && usable && lvl <= CAP - RNG_GROUP));
 	}
 
 	// Pop this lane's next pair (caller guarantees lvl >= 1 via ensure()).
