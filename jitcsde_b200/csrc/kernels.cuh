@@ -7,6 +7,9 @@
 namespace jsde {
 
 constexpr int BLOCK = 128;
+#ifndef JSDE_MIN_BLOCKS
+#define JSDE_MIN_BLOCKS 4  // resident blocks per SM the register allocator must leave room for
+#endif
 
 // ---- totals: warp-reduce, one atomic per warp -------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
@@ -64,7 +67,7 @@ __device__ __forceinline__ WarpRng<Model::N> make_rng(const EnsembleView &e, int
 // pairs an attempt may need and (b) one attempted step per such lane.  Choosing the next target and applying a jump
 // are folded into the same loop so that lanes which jump do not serialise the warp.
 template <class Model>
-__global__ void __launch_bounds__(BLOCK) k_integrate(EnsembleView e, Controller c, double target, int use_tape)
+__global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleView e, Controller c, double target, int use_tape)
 {
 	constexpr int N = Model::N;
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;

@@ -31,9 +31,10 @@ template <int N>
 struct WarpRng {
 	// room for the pairs left over below one draw's need (N-1) plus a full group
 	static constexpr int CAP = N - 1 + RNG_GROUP;
-	static constexpr int SMEM_DOUBLES_PER_WARP = 3 * CAP * RNG_STRIDE;
+	static constexpr int SMEM_DOUBLES_PER_WARP = 3 * CAP * RNG_STRIDE + 4;
 
 	double *fx1, *fx2, *fr2;  // this warp's FIFO arrays [CAP][RNG_STRIDE]
+	unsigned char *order;     // this warp's scratch list of lanes being served (32 bytes)
 	uint4 *S0;                // generator record of the warp's lane-0 trajectory
 	int lane;
 	int rd, lvl, chunk;       // this lane's FIFO read slot / fill level, its trajectory's next chunk
@@ -41,7 +42,7 @@ struct WarpRng {
 
 	__device__ __forceinline__ WarpRng(double *smem_warp, uint4 *mt, int64_t k_lane0, bool live)
 		: fx1(smem_warp), fx2(smem_warp + CAP * RNG_STRIDE), fr2(smem_warp + 2 * CAP * RNG_STRIDE),
-		  S0(mt + k_lane0 * MT_CHUNKS), lane(threadIdx.x & 31), rd(0), lvl(0), chunk(0), usable(live) {}
+		  order(reinterpret_cast<unsigned char *>(smem_warp + 3 * CAP * RNG_STRIDE)), S0(mt + k_lane0 * MT_CHUNKS), lane(threadIdx.x & 31), rd(0), lvl(0), chunk(0), usable(live) {}
 
 	// ---- persistence across kernel launches: spill [CAP][3][B] + level; read slot is normalised to 0 ---------------
 	__device__ __forceinline__ void load(const double *spill, const int *levels, const int *chunks, int64_t B, int64_t k)
@@ -78,100 +79,121 @@ struct WarpRng {
 
 	// ---- cooperative refill ------------------------------------------------------------------------------------------
 	// `room` = lanes whose FIFO can take a full group.  They are served four at a time ("slot": 4 trajectories x 8
-	// candidates), each exactly once.  Pass 1 only prefetches every slot's state lines into L1 so that the memory
-	// latency is paid once per refill, not once per slot; pass 2 does the work.  Both are run-time loops: unrolling
-	// them blew the 32 KB instruction cache (profiles/r01_v3_*: 40 % of stall samples were instruction fetch).
-	__device__ __forceinline__ void refill(unsigned room)
+	// candidates), each exactly once, in one run-time loop (unrolled variants blew the 32 KB instruction cache,
+	// profiles/r01_v3_*).  The loop is software-pipelined: the state words of slot s+1 are loaded into registers
+	// before slot s is processed, so only the first slot's load latency is exposed — and that one is usually an L1 hit
+	// because the previous refill ended by prefetching the lines its successor will start with.
+	struct SlotWords {
+		uint4 a, tap;
+		uint32_t edge_next, edge_tap;
+		int T, c;
+		bool have;
+	};
+
+	__device__ __forceinline__ int served_lane(int rank) const { return order[rank]; }
+
+	__device__ __forceinline__ SlotWords fetch(int s, int nserved, int g, int j) const
+	{
+		SlotWords w;
+		const int rank = 4 * s + g;
+		w.have = rank < nserved;
+		w.T = w.have ? order[rank] : 0;
+		w.c = mt_wrap(__shfl_sync(0xffffffffu, chunk, w.T) + j);
+		w.a = make_uint4(0, 0, 0, 0);
+		w.tap = make_uint4(0, 0, 0, 0);
+		w.edge_next = 0;
+		w.edge_tap = 0;
+		if (w.have) {
+			const uint4 *ST = S0 + w.T * MT_CHUNKS;
+			w.a = ST[w.c];
+			w.tap = ST[mt_wrap(w.c + 99)];
+			if (j == RNG_GROUP - 1) {
+				w.edge_next = reinterpret_cast<const uint32_t *>(ST + mt_wrap(w.c + 1))[0];
+				w.edge_tap = reinterpret_cast<const uint32_t *>(ST + mt_wrap(w.c + 100))[0];
+			}
+		}
+		return w;
+	}
+
+	__device__ __forceinline__ void refill(unsigned room, unsigned next_room_guess)
 	{
 		const unsigned full = 0xffffffffu;
 		const int g = lane >> 3, j = lane & 7;
-		const int slots = (__popc(room) + 3) >> 2;
-		// rank-(4s+g) set bit of `room` for slot s: strip g lowest bits once, then 4 more per slot
-		unsigned m0 = room;
-		if (g >= 1) m0 &= m0 - 1;
-		if (g >= 2) m0 &= m0 - 1;
-		if (g >= 3) m0 &= m0 - 1;
-		if (slots > 1) {
-			unsigned m = m0;
-#pragma unroll 1
-			for (int s = 0; s < slots; s++) {
-				const bool have = m != 0;
-				const int T = have ? __ffs(m) - 1 : 0;
-				m &= m - 1; m &= m - 1; m &= m - 1; m &= m - 1;
-				const int c = mt_wrap(__shfl_sync(full, chunk, T) + j);
-				if (have) {
-					const uint4 *ST = S0 + (int64_t)T * MT_CHUNKS;
-					prefetch_l1(ST + c);
-					prefetch_l1(ST + mt_wrap(c + 99));
-					if (j == RNG_GROUP - 1) {
-						prefetch_l1(ST + mt_wrap(c + 1));
-						prefetch_l1(ST + mt_wrap(c + 100));
-					}
-				}
-			}
-		}
-		const int below = __popc(room & ((1u << lane) - 1u));
+		const int nserved = __popc(room);
+		const int slots = (nserved + 3) >> 2;
+		const unsigned lt = (1u << lane) - 1u;
+		const int below = __popc(room & lt);
+		const bool mine_served = (room >> lane) & 1u;
+		if (mine_served)
+			order[below] = (unsigned char)lane;  // compacted list of the lanes to serve
+		__syncwarp();
 		int mine = 0;
-		unsigned m = m0;
+		SlotWords w = fetch(0, nserved, g, j);
 #pragma unroll 1
 		for (int s = 0; s < slots; s++) {
-			const bool have = m != 0;
-			const int T = have ? __ffs(m) - 1 : 0;
-			m &= m - 1; m &= m - 1; m &= m - 1; m &= m - 1;
-			uint4 *ST = S0 + (int64_t)T * MT_CHUNKS;
-			const int c = mt_wrap(__shfl_sync(full, chunk, T) + j);
-			const int rdT = __shfl_sync(full, rd, T);
-			const int lvT = __shfl_sync(full, lvl, T);
-			uint4 a = make_uint4(0, 0, 0, 0), tap = make_uint4(0, 0, 0, 0);
-			uint32_t edge_next = 0, edge_tap = 0;
-			if (have) {
-				a = ST[c];
-				tap = ST[mt_wrap(c + 99)];
-				if (j == RNG_GROUP - 1) {
-					edge_next = reinterpret_cast<const uint32_t *>(ST + mt_wrap(c + 1))[0];
-					edge_tap = reinterpret_cast<const uint32_t *>(ST + mt_wrap(c + 100))[0];
-				}
-			}
-			uint32_t next = __shfl_down_sync(full, a.x, 1);
-			uint32_t tap_hi = __shfl_down_sync(full, tap.x, 1);
+			SlotWords nx;
+			if (s + 1 < slots)  // warp-uniform
+				nx = fetch(s + 1, nserved, g, j);
+			const int rdT = __shfl_sync(full, rd, w.T);
+			const int lvT = __shfl_sync(full, lvl, w.T);
+			uint32_t next = __shfl_down_sync(full, w.a.x, 1);
+			uint32_t tap_hi = __shfl_down_sync(full, w.tap.x, 1);
 			if (j == RNG_GROUP - 1) {
-				next = edge_next;
-				tap_hi = edge_tap;
+				next = w.edge_next;
+				tap_hi = w.edge_tap;
 			}
 			bool ok = false;
 			double x1 = 0.0, x2 = 0.0, r2 = 0.0;
-			if (have) {
+			if (w.have) {
 				uint4 r;
-				r.x = tap.y ^ mt_mix(a.x, a.y);
-				r.y = tap.z ^ mt_mix(a.y, a.z);
-				r.z = tap.w ^ mt_mix(a.z, a.w);
-				r.w = tap_hi ^ mt_mix(a.w, next);
-				ST[c] = r;
-				a.x = mt_temper(a.x);
-				a.y = mt_temper(a.y);
-				a.z = mt_temper(a.z);
-				a.w = mt_temper(a.w);
-				ok = polar_candidate(a, x1, x2, r2);
+				r.x = w.tap.y ^ mt_mix(w.a.x, w.a.y);
+				r.y = w.tap.z ^ mt_mix(w.a.y, w.a.z);
+				r.z = w.tap.w ^ mt_mix(w.a.z, w.a.w);
+				r.w = tap_hi ^ mt_mix(w.a.w, next);
+				S0[w.T * MT_CHUNKS + w.c] = r;
+				uint4 v;
+				v.x = mt_temper(w.a.x);
+				v.y = mt_temper(w.a.y);
+				v.z = mt_temper(w.a.z);
+				v.w = mt_temper(w.a.w);
+				ok = polar_candidate(v, x1, x2, r2);
 			}
 			const unsigned okm = __ballot_sync(full, ok);
 			const unsigned grp = (okm >> (g * RNG_GROUP)) & 0xffu;
-			const int rank = __popc(grp & ((1u << j) - 1u));
-			const int cnt = __popc(grp);
 			if (ok) {
-				int slot = rdT + lvT + rank;
+				int slot = rdT + lvT + __popc(grp & ((1u << j) - 1u));
 				slot = slot >= CAP ? slot - CAP : slot;
-				fx1[slot * RNG_STRIDE + T] = x1;
-				fx2[slot * RNG_STRIDE + T] = x2;
-				fr2[slot * RNG_STRIDE + T] = r2;
+				const int at = slot * RNG_STRIDE + w.T;
+				fx1[at] = x1;
+				fx2[at] = x2;
+				fr2[at] = r2;
 			}
-			// owner: the lane whose trajectory has rank r among `room` is served by slot r/4, group r%4
-			const int v = __shfl_sync(full, cnt, (below & 3) * RNG_GROUP);
+			// owner: the lane whose trajectory has rank r among `room` was served by slot r/4, group r%4
 			if ((below >> 2) == s)
-				mine = v;
+				mine = __popc((okm >> ((below & 3) * RNG_GROUP)) & 0xffu);
+			if (s + 1 < slots)
+				w = nx;
 		}
-		if ((room >> lane) & 1u) {
+		if (mine_served) {
 			lvl += mine;
 			chunk = mt_wrap(chunk + RNG_GROUP);
+		}
+		// tail: pull the lines the next refill's first slot will want into L1 while the warp goes off to step
+		{
+			const int rank = __popc(next_room_guess & lt);
+			const bool first4 = ((next_room_guess >> lane) & 1u) && rank < 4;
+			const unsigned m4 = __ballot_sync(full, first4);
+			unsigned m = m4;
+			if (g >= 1) m &= m - 1;
+			if (g >= 2) m &= m - 1;
+			if (g >= 3) m &= m - 1;
+			const int T = m ? __ffs(m) - 1 : 0;
+			const int c = mt_wrap(__shfl_sync(full, chunk, T) + j);
+			if (m) {
+				const uint4 *ST = S0 + T * MT_CHUNKS;
+				prefetch_l1(ST + c);
+				prefetch_l1(ST + mt_wrap(c + 99));
+			}
 		}
 		__syncwarp();
 	}
@@ -181,8 +203,14 @@ struct WarpRng {
 	__device__ __forceinline__ void ensure(bool wants, int need)
 	{
 		const unsigned full = 0xffffffffu;
-		while (__ballot_sync(full, wants && usable && lvl < need))
-			refill(__ballot_sync(full, wants && usable && lvl <= CAP - RNG_GROUP));
+		while (__ballot_sync(full, wants && usable && lvl < need)) {
+			const bool ok = wants && usable;
+			const unsigned room = __ballot_sync(full, ok && lvl <= CAP - RNG_GROUP);
+			// after this refill a served lane holds about lvl+6 pairs and then consumes `need`: who has room next time?
+			const bool served = (room >> lane) & 1u;
+			const unsigned guess = __ballot_sync(full, ok && (served ? lvl + 6 : lvl) - need <= CAP - RNG_GROUP);
+			refill(room, guess);
+		}
 	}
 
 	// Pop this lane's next pair (caller guarantees lvl >= 1 via ensure()).
