@@ -6,8 +6,8 @@
 //   y        [n][B]      state                                   (reference: sde_integrator.state, template:29)
 //   t, dt    [B]         time, controller step size              (template:30; _jitcsde.py self.dt)
 //   new_y, err [n][B], new_t [B]   last proposal                 (template:31-33) — only the single-step surface uses them
-//   q_h      [D][B]      noise memory: length of item d          (template:15-21, as a bounded array instead of a list;
-//   q_w      [D][2n][B]  its DW (rows 0..n-1) and DZ (n..2n-1)    item 0 always starts at the current time)
+//   q        [D][B][IT]  noise memory (template:15-21) as a bounded array instead of a list: item d of trajectory b is
+//                        {h, DW[n], DZ[n]} padded to IT = 2*ceil((1+2n)/2) doubles; item 0 starts at the current time
 //   q_count, q_cursor [B]
 //   mt       [B][156] uint4   generator state, one contiguous 2496-byte record per trajectory (random_numbers.c:31-38);
 //                             positions of different trajectories drift apart (rejections), so records are lane-private
@@ -21,6 +21,8 @@
 #include <stdint.h>
 
 namespace jsde {
+
+__host__ __device__ constexpr int noise_item_doubles(int n) { return (1 + 2 * n + 1) & ~1; }
 
 struct Controller {
 	double atol, rtol, min_step, max_step, dec_thr, inc_thr, safety, max_factor, min_factor;
@@ -39,7 +41,7 @@ struct EnsembleView {
 	int D;  // noise capacity (items)
 	double *y, *t, *dt;
 	double *new_y, *err, *new_t;
-	double *q_h, *q_w;
+	double *q;  // [D][B][IT]
 	int *q_count, *q_cursor;
 	uint4 *mt;
 	int *mt_chunk;

@@ -177,7 +177,7 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 #define ALLOC(ptr, cnt) if ((rc = dev_alloc(h, &(ptr), (size_t)(cnt)))) return bail(rc)
 	ALLOC(v.y, B * n); ALLOC(v.t, B); ALLOC(v.dt, B);
 	ALLOC(v.new_y, B * n); ALLOC(v.err, B * n); ALLOC(v.new_t, B);
-	ALLOC(v.q_h, (int64_t)h->D * B); ALLOC(v.q_w, (int64_t)h->D * 2 * n * B);
+	ALLOC(v.q, (int64_t)h->D * B * noise_item_doubles(n));
 	ALLOC(v.q_count, B); ALLOC(v.q_cursor, B);
 	ALLOC(v.mt, B * MT_CHUNKS); ALLOC(v.mt_chunk, B);
 	ALLOC(v.rng_spill, (int64_t)WarpRng<Model::N>::CAP * 3 * B); ALLOC(v.rng_level, B);
@@ -514,11 +514,8 @@ int jsde_dump_noise(jsde_t *h, int64_t b, double *out_host, int max_items, int *
 	CU(cudaStreamSynchronize(h->stream));
 	CU(cudaMemcpy(count, h->v.q_count + b, sizeof(int), cudaMemcpyDeviceToHost));
 	const int width = 1 + 2 * n;
-	for (int d = 0; d < *count && d < max_items; d++) {
-		CU(cudaMemcpy(out_host + (size_t)d * width, h->v.q_h + (int64_t)d * h->B + b, sizeof(double), cudaMemcpyDeviceToHost));
-		for (int c = 0; c < 2 * n; c++)
-			CU(cudaMemcpy(out_host + (size_t)d * width + 1 + c, h->v.q_w + ((int64_t)d * 2 * n + c) * h->B + b, sizeof(double), cudaMemcpyDeviceToHost));
-	}
+	for (int d = 0; d < *count && d < max_items; d++)
+		CU(cudaMemcpy(out_host + (size_t)d * width, h->v.q + ((int64_t)d * h->B + b) * noise_item_doubles(n), width * sizeof(double), cudaMemcpyDeviceToHost));
 	return JSDE_OK;
 }
 

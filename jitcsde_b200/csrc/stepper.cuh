@@ -27,8 +27,10 @@ struct Lane {
 
 	const EnsembleView &e;
 	const int64_t k;
+	static constexpr int IT = noise_item_doubles(N);  // one noise item: {h, DW[N], DZ[N]} padded to 16-byte pairs
+
 	WarpRng<N> &rng;
-	double *const qh0, *const qw0;  // this trajectory's column of the noise-memory arrays
+	double *const q0;  // item 0 of this trajectory's noise memory; item d is at q0 + d*B*IT
 
 	double y[N], t, dt;
 	double ny[N], er[N], nt;  // last proposal
@@ -38,11 +40,56 @@ struct Lane {
 	int max_depth;
 
 	__device__ __forceinline__ Lane(const EnsembleView &view, int64_t index, WarpRng<N> &source)
-		: e(view), k(index), rng(source), qh0(view.q_h + index), qw0(view.q_w + index), fresh(0), max_depth(0) {}
+		: e(view), k(index), rng(source), q0(view.q + index * IT), fresh(0), max_depth(0) {}
 
 	// ---- global-memory accessors ---------------------------------------------------------------------------
-	__device__ __forceinline__ double &qh(int d) const { return qh0[(int64_t)d * e.B]; }
-	__device__ __forceinline__ double &qw(int d, int c) const { return qw0[(int64_t)(d * (2 * N) + c) * e.B]; }
+	// Noise memory: items of IT doubles, [D][B][IT]; a warp's 32 items of one depth are 32*IT*8 contiguous bytes and an
+	// item moves as IT/2 16-byte vectors.
+	__device__ __forceinline__ double *item_ptr(int d) const { return q0 + (int64_t)d * e.B * IT; }
+
+	__device__ __forceinline__ void load_item(int d, double &h, double (&W)[N], double (&Z)[N]) const
+	{
+		const double2 *p = reinterpret_cast<const double2 *>(item_ptr(d));
+		double v[IT];
+#pragma unroll
+		for (int i = 0; i < IT / 2; i++) {
+			const double2 t = p[i];
+			v[2 * i] = t.x;
+			v[2 * i + 1] = t.y;
+		}
+		h = v[0];
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			W[i] = v[1 + i];
+			Z[i] = v[1 + N + i];
+		}
+	}
+
+	__device__ __forceinline__ void store_item(int d, double h, const double (&W)[N], const double (&Z)[N]) const
+	{
+		double2 *p = reinterpret_cast<double2 *>(item_ptr(d));
+		double v[IT];
+		v[0] = h;
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			v[1 + i] = W[i];
+			v[1 + N + i] = Z[i];
+		}
+		if (IT > 1 + 2 * N)
+			v[IT - 1] = 0.0;
+#pragma unroll
+		for (int i = 0; i < IT / 2; i++)
+			p[i] = make_double2(v[2 * i], v[2 * i + 1]);
+	}
+
+	__device__ __forceinline__ void move_item(int to, int from) const
+	{
+		const double2 *src = reinterpret_cast<const double2 *>(item_ptr(from));
+		double2 *dst = reinterpret_cast<double2 *>(item_ptr(to));
+#pragma unroll 1
+		for (int i = 0; i < IT / 2; i++)
+			dst[i] = src[i];
+	}
 
 	__device__ __forceinline__ void load()
 	{
@@ -137,38 +184,41 @@ struct Lane {
 		bool started = false;
 		double need = h;
 		int cur = 0;
+		double hq = 0.0, qW[N], qZ[N];  // item at the cursor (valid when cur < count)
+		bool have_item = false;
 		while (need != 0.0 && cur < count) {
-			const double hq = qh(cur);
+			load_item(cur, hq, qW, qZ);
+			have_item = true;
 			if (!(hq <= need))
 				break;
 			if (started) {
 #pragma unroll
 				for (int i = 0; i < N; i++) {
-					W[i] += qw(cur, i);
-					Z[i] += qw(cur, N + i);
+					W[i] += qW[i];
+					Z[i] += qZ[i];
 				}
 			} else {
 				started = true;
 #pragma unroll
 				for (int i = 0; i < N; i++) {
-					W[i] = qw(cur, i);
-					Z[i] = qw(cur, N + i);
+					W[i] = qW[i];
+					Z[i] = qZ[i];
 				}
 			}
 			need -= hq;
 			cur++;
+			have_item = false;
 		}
 		if (need != 0.0) {
 			if (count >= e.D) {
 				status = TRAJ_NOISE_OVERFLOW;
 				return false;
 			}
-			const bool bridging = cur < count;
+			const bool bridging = cur < count;  // then the loop above left the too-long item in (hq, qW, qZ)
 			double h_exc = 0.0, factor = 0.0, scale;
 			if (bridging) {  // Brownian_bridge (template:178-202)
-				const double h_item = qh(cur);
-				h_exc = h_item - need;
-				factor = h_exc / h_item;
+				h_exc = hq - need;
+				factor = h_exc / hq;
 				scale = sqrt(factor * need);
 			} else  // append_noise (template:170-176)
 				scale = sqrt(need);
@@ -177,29 +227,20 @@ struct Lane {
 			fresh++;
 			if (bridging) {
 #pragma unroll 1
-				for (int d = count - 1; d > cur; d--) {  // make room behind the cursor (the reference relinks its list)
-					qh(d + 1) = qh(d);
-#pragma unroll 1
-					for (int c = 0; c < 2 * N; c++)
-						qw(d + 1, c) = qw(d, c);
-				}
+				for (int d = count - 1; d > cur; d--)  // make room behind the cursor (the reference relinks its list)
+					move_item(d + 1, d);
+				double w2[N], z2[N];
 #pragma unroll
 				for (int i = 0; i < N; i++) {
-					const double w1 = qw(cur, i), z1 = qw(cur, N + i);
-					const double w2 = gW[i] + w1 * factor, z2 = gZ[i] + z1 * factor;
-					gW[i] = w1 - w2;
-					gZ[i] = z1 - z2;
-					qw(cur + 1, i) = w2;
-					qw(cur + 1, N + i) = z2;
+					w2[i] = gW[i] + qW[i] * factor;
+					z2[i] = gZ[i] + qZ[i] * factor;
+					gW[i] = qW[i] - w2[i];
+					gZ[i] = qZ[i] - z2[i];
 				}
-				qh(cur + 1) = h_exc;
+				store_item(cur + 1, h_exc, w2, z2);
 			}
-			qh(cur) = need;
-#pragma unroll
-			for (int i = 0; i < N; i++) {
-				qw(cur, i) = gW[i];
-				qw(cur, N + i) = gZ[i];
-			}
+			(void)have_item;
+			store_item(cur, need, gW, gZ);
 			count++;
 			if (started) {
 #pragma unroll
@@ -237,12 +278,7 @@ struct Lane {
 		}
 		double gW[N], gZ[N];
 		draw(sqrt(step), gW, gZ);
-		qh(count) = step;
-#pragma unroll
-		for (int i = 0; i < N; i++) {
-			qw(count, i) = gW[i];
-			qw(count, N + i) = gZ[i];
-		}
+		store_item(count, step, gW, gZ);
 		count++;
 		cursor = count - 1;  // template:173: current_noise = the newest item, so an accept_step right after keeps only it
 		max_depth = count > max_depth ? count : max_depth;
@@ -346,12 +382,8 @@ struct Lane {
 		const int rest = count - cursor;
 		if (cursor > 0) {
 #pragma unroll 1
-			for (int d = 0; d < rest; d++) {
-				qh(d) = qh(d + cursor);
-#pragma unroll 1
-				for (int c = 0; c < 2 * N; c++)
-					qw(d, c) = qw(d + cursor, c);
-			}
+			for (int d = 0; d < rest; d++)
+				move_item(d, d + cursor);
 		}
 		count = rest;
 		cursor = 0;
