@@ -204,9 +204,11 @@ def run_gpu_arm(args):
 	B = 1 << args.log2_ensemble
 	spec = models.lorenz_additive
 	# global index k = rank*B + j decides y0 and seed, so results do not depend on the number of GPUs
-	y0 = np.random.default_rng(42).random(((rank + 1) * B, 3))[rank * B:]
+	from jitcsde_b200 import sharding
+	lo, hi = sharding.shard_range(world * B, rank, world)  # weak scaling: B per GPU
+	y0 = sharding.global_initial_states(lo, hi, 3)
 	y0_pinned = torch.from_numpy(np.ascontiguousarray(y0)).pin_memory()
-	seeds = (np.arange(rank * B, (rank + 1) * B, dtype=np.uint64)) & np.uint64(0xFFFFFFFF)
+	seeds = sharding.global_seeds(lo, hi)
 
 	SDE = jitcsde(spec=spec, ensemble=B, device=local, verbose=False)
 	SDE.set_seed(seeds)
@@ -306,7 +308,7 @@ def main():
 	ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
 	ap.add_argument("--log2-ensemble", type=int, default=20)
 	ap.add_argument("--t-end", type=float, default=100.0)
-	ap.add_argument("--cpu-per-core", type=int, default=16, help="trajectories per host core in one CPU-reference pass")
+	ap.add_argument("--cpu-per-core", type=int, default=192, help="trajectories per host core in one CPU-reference pass")
 	ap.add_argument("--no-cpu-baseline", action="store_true")
 	args = ap.parse_args()
 	if args.impl == "reference":

@@ -298,27 +298,23 @@ class jitcsde:
 			warn("`number` does not appear to be a integer. This is very likely cause an error immediately.", stacklevel=2)
 		self.SDE.pin_noise(number, step_size)
 
-	def ensemble_moments(self, process_group=None):
+	def ensemble_moments(self, process_group=None, shift=None):
 		"""
 		Mean and variance of the current state over the whole ensemble.  With `torch.distributed` initialised the
 		{count, Σ(y−c), Σ(y−c)²} accumulators are all-reduced (NCCL over NVLink) so every rank gets the moments of the
-		union of all shards (SURVEY.md §8 e).
+		union of all shards (SURVEY.md §8 e).  `shift` (c, length n) must be the same on every rank; default zeros.
 		"""
 		import torch
-		import torch.distributed as dist
+
+		from . import sharding
 
 		self._initiate()
 		dev = torch.device("cuda", self.device)
 		acc = torch.zeros(1 + 2 * self.n, dtype=torch.float64, device=dev)
-		shift = np.asarray(self._y[0], dtype=np.float64) * 0.0
+		shift = np.zeros(self.n) if shift is None else np.asarray(shift, dtype=np.float64)
 		self.SDE.moments_into(acc.data_ptr(), shift)
-		if dist.is_available() and dist.is_initialized():
-			dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=process_group)
-		a = acc.cpu().numpy()
-		count = a[0]
-		mean = a[1:1 + self.n] / count
-		var = (a[1 + self.n:] - count * mean ** 2) / (count - 1) if count > 1 else np.full(self.n, np.nan)
-		return dict(count=int(count), mean=mean + shift, var=var)
+		sharding.all_reduce_sum(acc, process_group)
+		return sharding.moments_from_accumulators(acc.cpu().numpy(), shift)
 
 
 class jitcsde_jump(jitcsde):
