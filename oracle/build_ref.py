@@ -94,15 +94,17 @@ def build(spec, flavour: str = "strict", force: bool = False) -> str:
 			fh.write(rendered)
 		shutil.copy(os.path.join(src_dir, "random_numbers.c"), tmp)
 		# control parameters: the reference substitutes `self->parameter_X` (`_jitcsde.py:388-391`)
+		# (as scoped macros inside the two generated bodies, so that a parameter called e.g. `k` cannot touch the template)
 		par_defs = "".join(f"#define {p} (self->parameter_{p})\n" for p in spec.control_pars)
+		par_undefs = "".join(f"#undef {p}\n" for p in spec.control_pars)
 		with open(os.path.join(tmp, "f_definitions.c"), "w") as fh:
-			fh.write(par_defs + spec.preamble)
+			fh.write(spec.preamble)
 		with open(os.path.join(tmp, "g_definitions.c"), "w") as fh:
 			fh.write("")
 		with open(os.path.join(tmp, "f.c"), "w") as fh:
-			fh.write(_statements("drift", spec.f, spec.f_body))
+			fh.write(par_defs + _statements("drift", spec.f, spec.f_body) + par_undefs)
 		with open(os.path.join(tmp, "g.c"), "w") as fh:
-			fh.write(_statements("diffusion", spec.g, spec.g_body))
+			fh.write(par_defs + _statements("diffusion", spec.g, spec.g_body) + par_undefs)
 		cmd = [
 			os.environ.get("CC", "gcc"), "-shared", "-fPIC", *FLAGS[flavour],
 			"-I" + sysconfig.get_paths()["include"], "-I" + numpy.get_include(),
