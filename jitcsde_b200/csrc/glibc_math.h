@@ -71,8 +71,10 @@ JSDE_FN double jsde_log_near_one(double x)
 	return JSDE_FMA(Q, r3, lo2) + hi;
 }
 
-// x = 2^k z, z in [0x1.69555p-1, 0x1.69555p0); table on the top 7 mantissa bits of z
-JSDE_FN double jsde_log_table(double x)
+// x = 2^k z, z in [0x1.69555p-1, 0x1.69555p0); table on the top 7 mantissa bits of z.  `tab` holds {invc, logc}
+// pairs (128 entries); the kernels pass a shared-memory copy so that the lookup does not queue behind outstanding
+// global-memory traffic.
+JSDE_FN double jsde_log_table_from(double x, const double *tab)
 {
 	const uint64_t ix = JSDE_ASU(x);
 	const uint64_t tmp = ix - 0x3fe6000000000000ULL;
@@ -81,8 +83,8 @@ JSDE_FN double jsde_log_table(double x)
 	const uint64_t iz = ix - (tmp & (0xfffULL << 52));
 	const double z = JSDE_ASD(iz);
 	const double kd = (double)k;
-	const double invc = JSDE_TAB(JSDE_LOG_INVC, i);
-	const double logc = JSDE_TAB(JSDE_LOG_LOGC, i);
+	const double invc = tab ? tab[2 * i] : JSDE_TAB(JSDE_LOG_INVC, i);
+	const double logc = tab ? tab[2 * i + 1] : JSDE_TAB(JSDE_LOG_LOGC, i);
 	const double w = JSDE_FMA(kd, JSDE_LN2HI, logc);
 	const double r = JSDE_FMA(z, invc, -1.0);
 	const double hi = w + r;
@@ -92,6 +94,8 @@ JSDE_FN double jsde_log_table(double x)
 	const double q = JSDE_FMA(JSDE_FMA(r, JSDE_LOG_A4, JSDE_LOG_A3), r2, JSDE_FMA(r, JSDE_LOG_A2, JSDE_LOG_A1));
 	return JSDE_FMA(r3, q, JSDE_FMA(r2, JSDE_LOG_A0, lo)) + hi;
 }
+
+JSDE_FN double jsde_log_table(double x) { return jsde_log_table_from(x, (const double *)0); }
 
 JSDE_FN double jsde_log(double x)
 {

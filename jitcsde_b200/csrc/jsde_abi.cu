@@ -204,6 +204,13 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	if ((rc = reset_integrator(h))) return bail(rc);
 	if ((err = cudaStreamSynchronize(h->stream)) != cudaSuccess)
 		return bail(fail(JSDE_E_CUDA, cudaGetErrorString(err)));
+	// the generator FIFOs + staging area exceed the 48 KB default for dynamic shared memory
+	const int smem = (int)rng_smem_bytes<Model>();
+	if ((err = cudaFuncSetAttribute(k_integrate<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+		(err = cudaFuncSetAttribute(k_get_next_step<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+		(err = cudaFuncSetAttribute(k_pin_noise<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+		(err = cudaFuncSetAttribute(k_draw_gauss<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+		return bail(fail(JSDE_E_CUDA, cudaGetErrorString(err)));
 	*out = h;
 	return JSDE_OK;
 }

@@ -51,15 +51,23 @@ __device__ __forceinline__ void add_totals(CallTotals *tot, unsigned long long a
 
 // ---- the hot path -------------------------------------------------------------------------------------------------
 // Shared memory: one set of generator FIFOs per warp (warp_rng.cuh).
-template <class Model>
-constexpr size_t rng_smem_bytes() { return (size_t)(BLOCK / 32) * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP * sizeof(double); }
+constexpr int LOG_TAB_DOUBLES = 256;  // {invc, logc}[128], shared by the block
 
+template <class Model>
+constexpr size_t rng_smem_bytes() { return ((size_t)(BLOCK / 32) * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP + LOG_TAB_DOUBLES) * sizeof(double); }
+
+// Whole block must call (contains a __syncthreads).
 template <class Model>
 __device__ __forceinline__ WarpRng<Model::N> make_rng(const EnsembleView &e, int64_t k, bool live)
 {
-	extern __shared__ double jsde_smem[];
+	extern __shared__ __align__(16) double jsde_smem[];
+	for (int i = threadIdx.x; i < 128; i += BLOCK) {
+		jsde_smem[2 * i] = JSDE_LOG_INVC[i];
+		jsde_smem[2 * i + 1] = JSDE_LOG_LOGC[i];
+	}
+	__syncthreads();
 	const int warp = threadIdx.x >> 5;
-	return WarpRng<Model::N>(jsde_smem + warp * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP, e.mt, k - (threadIdx.x & 31), live);
+	return WarpRng<Model::N>(jsde_smem + LOG_TAB_DOUBLES + warp * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP, jsde_smem, e.mt, k - (threadIdx.x & 31), live);
 }
 
 // jitcsde.integrate (_jitcsde.py:597-630) and, with a tape, jitcsde_jump.integrate (:693-700) for every trajectory.
@@ -76,7 +84,7 @@ __global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleVi
 	WarpRng<N> rng = make_rng<Model>(e, k, live);
 	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 	Lane<Model> L(e, kk, rng);
-	unsigned long long acc = 0, rej = 0, jumps = 0;
+	unsigned acc = 0, rej = 0, jumps = 0;  // per call and trajectory: far below 2^32 (the noise memory would overflow first)
 	double next_jump = 0.0;
 	bool jump_set = false;
 	long long tape_pos = 0;
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(BLOCK) k_get_p(EnsembleView e, double atol, do
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B)
 		return;
-	WarpRng<Model::N> rng(nullptr, e.mt, 0, false);
+	WarpRng<Model::N> rng(nullptr, nullptr, e.mt, 0, false);
 	Lane<Model> L(e, k, rng);
 	L.load_proposal();
 	p[k] = L.error_ratio(atol, rtol);
@@ -233,7 +241,7 @@ __global__ void __launch_bounds__(BLOCK) k_accept_step(EnsembleView e, const uns
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B || (mask && !mask[k]))
 		return;
-	WarpRng<Model::N> rng(nullptr, e.mt, 0, false);
+	WarpRng<Model::N> rng(nullptr, nullptr, e.mt, 0, false);
 	Lane<Model> L(e, k, rng);
 	L.load();
 	L.load_proposal();
@@ -277,7 +285,8 @@ __global__ void __launch_bounds__(BLOCK) k_draw_gauss(EnsembleView e, double sca
 		if (live) {
 			double x1, x2, r2;
 			rng.pop(x1, x2, r2);
-			const double f = scale * polar_radius_factor(r2);
+			const double lg = jsde_log_is_near_one(r2) ? jsde_log_near_one(r2) : jsde_log_table_from(r2, rng.log_tab);
+			const double f = scale * sqrt(__ddiv_rn(__dmul_rn(-2.0, lg), r2));
 			out[(k * pairs + j) * 2] = x1 * f;
 			out[(k * pairs + j) * 2 + 1] = x2 * f;
 		}

@@ -149,7 +149,7 @@ struct Lane {
 #pragma unroll
 		for (int i = 0; i < N; i++) {
 			rng.pop(gW[i], gZ[i], r2[i]);
-			lg[i] = jsde_log_table(r2[i]);  // convergent; overwritten below for the ~6 % near-one radii
+			lg[i] = jsde_log_table_from(r2[i], rng.log_tab);  // convergent; overwritten below for the ~6 % near-one radii
 			if (jsde_log_is_near_one(r2[i]))
 				pending |= 1u << i;
 		}
@@ -292,14 +292,11 @@ struct Lane {
 			return false;
 		double arg[N], fh1[N], fh2[N], g1[N], g2[N];
 		if constexpr (!ADDITIVE) {
-			double I11s[N], I111[N], g3[N], g4[N];
+			double g3[N], g4[N];
 			const double sqh = sqrt(h);
 #pragma unroll
-			for (int i = 0; i < N; i++) {  // template:283-290
-				I11s[i] = (I1[i] * I1[i] - h) * 0.5 / sqh;
-				I111[i] = (I1[i] * I1[i] * I1[i] - 3 * h * I1[i]) * (1. / 6.);
+			for (int i = 0; i < N; i++)  // template:289; I_11/sqrt(h) and I_111 (:286-287) are formed where they are used
 				I10[i] = (I1[i] + DZ[i] * (1. / 1.7320508075688772)) * (h / 2.);
-			}
 			Model::drift(t, y, h, par, fh1);
 			Model::diffusion(t, y, par, g1);
 #pragma unroll
@@ -320,16 +317,18 @@ struct Lane {
 			Model::diffusion(t + 0.25 * h, arg, par, g4);
 #pragma unroll
 			for (int i = 0; i < N; i++) {  // template:447-464
+				const double I11s = (I1[i] * I1[i] - h) * 0.5 / sqh;
+				const double I111 = (I1[i] * I1[i] * I1[i] - 3 * h * I1[i]) * (1. / 6.);
 				const double E_N = (1. / h / 3.) * (
-					+ (6 * I10[i] - 6 * I111[i]) * g1[i]
-					+ (-4 * I10[i] + 5 * I111[i]) * g2[i]
-					+ (-2 * I10[i] - 2 * I111[i]) * g3[i]
-					+ (3 * I111[i]) * g4[i]);
+					+ (6 * I10[i] - 6 * I111) * g1[i]
+					+ (-4 * I10[i] + 5 * I111) * g2[i]
+					+ (-2 * I10[i] - 2 * I111) * g3[i]
+					+ (3 * I111) * g4[i]);
 				ny[i] = y[i] + E_N + (1. / 3.) * (
 					fh1[i] + 2 * fh2[i]
-					+ (-3 * I1[i] - 3 * I11s[i]) * g1[i]
-					+ (4 * I1[i] + 4 * I11s[i]) * g2[i]
-					+ (2 * I1[i] - I11s[i]) * g3[i]);
+					+ (-3 * I1[i] - 3 * I11s) * g1[i]
+					+ (4 * I1[i] + 4 * I11s) * g2[i]
+					+ (2 * I1[i] - I11s) * g3[i]);
 				const double E_D = (fh2[i] - fh1[i]) / 6;
 				er[i] = fabs(E_D) + fabs(E_N);
 			}

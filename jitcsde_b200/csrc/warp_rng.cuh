@@ -25,37 +25,56 @@ namespace jsde {
 constexpr int RNG_GROUP = 8;     // candidates per trajectory per op
 constexpr int RNG_STRIDE = 33;   // row stride (doubles) of the FIFO arrays: conflict-free column writes
 
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// 16-byte asynchronous copy global -> shared (LDGSTS): no register, no scoreboard wait until cp_async_wait_all()
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+	const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int RNG_STAGE_ENTRIES = 16;  // trajectories whose next state words are staged one phase ahead
+constexpr int RNG_STAGE_CHUNKS = 18;   // per entry: chunks c..c+8 and c+99..c+107
 
 template <int N>
 struct WarpRng {
 	// room for the pairs left over below one draw's need (N-1) plus a full group
 	static constexpr int CAP = N - 1 + RNG_GROUP;
-	static constexpr int SMEM_DOUBLES_PER_WARP = 3 * CAP * RNG_STRIDE + 4;
+	static constexpr int FIFO_DOUBLES = (3 * CAP * RNG_STRIDE + 1) & ~1;  // even: keeps the staging area 16-byte aligned
+	// FIFOs | order_()[32] bytes | stage_of_()[32] bytes | staged state words
+	static constexpr int SMEM_DOUBLES_PER_WARP = FIFO_DOUBLES + 4 + 4 + RNG_STAGE_ENTRIES * RNG_STAGE_CHUNKS * 2;
 
-	double *fx1, *fx2, *fr2;  // this warp's FIFO arrays [CAP][RNG_STRIDE]
-	unsigned char *order;     // this warp's scratch list of lanes being served (32 bytes)
+	double *fx1;              // this warp's shared memory: FIFO arrays x1, x2, r2, each [CAP][RNG_STRIDE], then ...
+	const double *log_tab;    // block-shared copy of glibc's log table {invc, logc}[128]
+	__device__ __forceinline__ double *fx2_() const { return fx1 + CAP * RNG_STRIDE; }
+	__device__ __forceinline__ double *fr2_() const { return fx1 + 2 * CAP * RNG_STRIDE; }
+	// ... order_()[32]: scratch list of lanes being served; stage_of_()[32]: staging entry of each lane's trajectory (0xFF:
+	// none); stage[RNG_STAGE_ENTRIES][RNG_STAGE_CHUNKS]: staged state words
+	__device__ __forceinline__ unsigned char *order_() const { return reinterpret_cast<unsigned char *>(fx1 + FIFO_DOUBLES); }
+	__device__ __forceinline__ unsigned char *stage_of_() const { return reinterpret_cast<unsigned char *>(fx1 + FIFO_DOUBLES + 4); }
+	__device__ __forceinline__ uint4 *stage_() const { return reinterpret_cast<uint4 *>(fx1 + FIFO_DOUBLES + 8); }
 	uint4 *S0;                // generator record of the warp's lane-0 trajectory
 	int lane;
 	int rd, lvl, chunk;       // this lane's FIFO read slot / fill level, its trajectory's next chunk
 	bool usable;              // lane owns a real trajectory
 
-	__device__ __forceinline__ WarpRng(double *smem_warp, uint4 *mt, int64_t k_lane0, bool live)
-		: fx1(smem_warp), fx2(smem_warp + CAP * RNG_STRIDE), fr2(smem_warp + 2 * CAP * RNG_STRIDE),
-		  order(reinterpret_cast<unsigned char *>(smem_warp + 3 * CAP * RNG_STRIDE)), S0(mt + k_lane0 * MT_CHUNKS), lane(threadIdx.x & 31), rd(0), lvl(0), chunk(0), usable(live) {}
+	__device__ __forceinline__ WarpRng(double *smem_warp, const double *shared_log_tab, uint4 *mt, int64_t k_lane0, bool live)
+		: fx1(smem_warp), log_tab(shared_log_tab), S0(mt + k_lane0 * MT_CHUNKS), lane(threadIdx.x & 31), rd(0), lvl(0), chunk(0), usable(live) {}
 
 	// ---- persistence across kernel launches: spill [CAP][3][B] + level; read slot is normalised to 0 ---------------
 	__device__ __forceinline__ void load(const double *spill, const int *levels, const int *chunks, int64_t B, int64_t k)
 	{
 		rd = 0;
 		lvl = 0;
+		stage_of_()[lane] = 0xFF;
 		if (usable) {
 			lvl = levels[k];
 			chunk = chunks[k];
 			for (int i = 0; i < lvl; i++) {
 				fx1[i * RNG_STRIDE + lane] = spill[((int64_t)i * 3 + 0) * B + k];
-				fx2[i * RNG_STRIDE + lane] = spill[((int64_t)i * 3 + 1) * B + k];
-				fr2[i * RNG_STRIDE + lane] = spill[((int64_t)i * 3 + 2) * B + k];
+				fx2_()[i * RNG_STRIDE + lane] = spill[((int64_t)i * 3 + 1) * B + k];
+				fr2_()[i * RNG_STRIDE + lane] = spill[((int64_t)i * 3 + 2) * B + k];
 			}
 		}
 		__syncwarp();
@@ -63,6 +82,7 @@ struct WarpRng {
 
 	__device__ __forceinline__ void store(double *spill, int *levels, int *chunks, int64_t B, int64_t k) const
 	{
+		cp_async_wait_all();  // staged words are simply dropped; the copies must not outlive the block
 		__syncwarp();
 		if (usable) {
 			levels[k] = lvl;
@@ -71,8 +91,8 @@ struct WarpRng {
 				int s = rd + i;
 				s = s >= CAP ? s - CAP : s;
 				spill[((int64_t)i * 3 + 0) * B + k] = fx1[s * RNG_STRIDE + lane];
-				spill[((int64_t)i * 3 + 1) * B + k] = fx2[s * RNG_STRIDE + lane];
-				spill[((int64_t)i * 3 + 2) * B + k] = fr2[s * RNG_STRIDE + lane];
+				spill[((int64_t)i * 3 + 1) * B + k] = fx2_()[s * RNG_STRIDE + lane];
+				spill[((int64_t)i * 3 + 2) * B + k] = fr2_()[s * RNG_STRIDE + lane];
 			}
 		}
 	}
@@ -90,50 +110,60 @@ struct WarpRng {
 		bool have;
 	};
 
-	__device__ __forceinline__ int served_lane(int rank) const { return order[rank]; }
+	__device__ __forceinline__ int served_lane(int rank) const { return order_()[rank]; }
 
 	__device__ __forceinline__ SlotWords fetch(int s, int nserved, int g, int j) const
 	{
 		SlotWords w;
 		const int rank = 4 * s + g;
 		w.have = rank < nserved;
-		w.T = w.have ? order[rank] : 0;
+		w.T = w.have ? order_()[rank] : 0;
 		w.c = mt_wrap(__shfl_sync(0xffffffffu, chunk, w.T) + j);
 		w.a = make_uint4(0, 0, 0, 0);
 		w.tap = make_uint4(0, 0, 0, 0);
 		w.edge_next = 0;
 		w.edge_tap = 0;
 		if (w.have) {
-			const uint4 *ST = S0 + w.T * MT_CHUNKS;
-			w.a = ST[w.c];
-			w.tap = ST[mt_wrap(w.c + 99)];
-			if (j == RNG_GROUP - 1) {
-				w.edge_next = reinterpret_cast<const uint32_t *>(ST + mt_wrap(w.c + 1))[0];
-				w.edge_tap = reinterpret_cast<const uint32_t *>(ST + mt_wrap(w.c + 100))[0];
+			const int e = stage_of_()[w.T];
+			if (e != 0xFF) {  // staged by the previous refill's tail: already in shared memory
+				const uint4 *E = stage_() + e * RNG_STAGE_CHUNKS;
+				w.a = E[j];
+				w.tap = E[9 + j];
+				if (j == RNG_GROUP - 1) {
+					w.edge_next = E[8].x;
+					w.edge_tap = E[17].x;
+				}
+			} else {
+				const uint4 *ST = S0 + w.T * MT_CHUNKS;
+				w.a = ST[w.c];
+				w.tap = ST[mt_wrap(w.c + 99)];
+				if (j == RNG_GROUP - 1) {
+					w.edge_next = reinterpret_cast<const uint32_t *>(ST + mt_wrap(w.c + 1))[0];
+					w.edge_tap = reinterpret_cast<const uint32_t *>(ST + mt_wrap(w.c + 100))[0];
+				}
 			}
 		}
 		return w;
 	}
 
-	__device__ __forceinline__ void refill(unsigned room, unsigned next_room_guess)
+	__device__ __forceinline__ void refill(unsigned room, bool wants, int need)
 	{
 		const unsigned full = 0xffffffffu;
 		const int g = lane >> 3, j = lane & 7;
+		cp_async_wait_all();  // words staged by the previous refill's tail
+		__syncwarp();
 		const int nserved = __popc(room);
 		const int slots = (nserved + 3) >> 2;
 		const unsigned lt = (1u << lane) - 1u;
 		const int below = __popc(room & lt);
 		const bool mine_served = (room >> lane) & 1u;
 		if (mine_served)
-			order[below] = (unsigned char)lane;  // compacted list of the lanes to serve
+			order_()[below] = (unsigned char)lane;  // compacted list of the lanes to serve
 		__syncwarp();
 		int mine = 0;
-		SlotWords w = fetch(0, nserved, g, j);
 #pragma unroll 1
 		for (int s = 0; s < slots; s++) {
-			SlotWords nx;
-			if (s + 1 < slots)  // warp-uniform
-				nx = fetch(s + 1, nserved, g, j);
+			const SlotWords w = fetch(s, nserved, g, j);  // usually from the staging area: no global-memory latency here
 			const int rdT = __shfl_sync(full, rd, w.T);
 			const int lvT = __shfl_sync(full, lvl, w.T);
 			uint32_t next = __shfl_down_sync(full, w.a.x, 1);
@@ -165,35 +195,48 @@ struct WarpRng {
 				slot = slot >= CAP ? slot - CAP : slot;
 				const int at = slot * RNG_STRIDE + w.T;
 				fx1[at] = x1;
-				fx2[at] = x2;
-				fr2[at] = r2;
+				fx2_()[at] = x2;
+				fr2_()[at] = r2;
 			}
 			// owner: the lane whose trajectory has rank r among `room` was served by slot r/4, group r%4
 			if ((below >> 2) == s)
 				mine = __popc((okm >> ((below & 3) * RNG_GROUP)) & 0xffu);
-			if (s + 1 < slots)
-				w = nx;
 		}
 		if (mine_served) {
 			lvl += mine;
 			chunk = mt_wrap(chunk + RNG_GROUP);
 		}
-		// tail: pull the lines the next refill's first slot will want into L1 while the warp goes off to step
+		// tail: stage the state words of the trajectories that will have room after their next draw (the refill that
+		// follows will serve exactly those) with asynchronous copies, so that their HBM latency overlaps the step phase
+		__syncwarp();  // everybody is done reading `order`, `stage_of` and `stage`
 		{
-			const int rank = __popc(next_room_guess & lt);
-			const bool first4 = ((next_room_guess >> lane) & 1u) && rank < 4;
-			const unsigned m4 = __ballot_sync(full, first4);
-			unsigned m = m4;
-			if (g >= 1) m &= m - 1;
-			if (g >= 2) m &= m - 1;
-			if (g >= 3) m &= m - 1;
-			const int T = m ? __ffs(m) - 1 : 0;
-			const int c = mt_wrap(__shfl_sync(full, chunk, T) + j);
-			if (m) {
-				const uint4 *ST = S0 + T * MT_CHUNKS;
-				prefetch_l1(ST + c);
-				prefetch_l1(ST + mt_wrap(c + 99));
+			const bool will = wants && lvl - need <= CAP - RNG_GROUP;
+			const unsigned sm = __ballot_sync(full, will);
+			const int rank = __popc(sm & lt);
+			const bool staged = will && rank < RNG_STAGE_ENTRIES;
+			stage_of_()[lane] = staged ? (unsigned char)rank : (unsigned char)0xFF;
+			if (staged)
+				order_()[rank] = (unsigned char)lane;
+			__syncwarp();
+			const int nstage = min(__popc(sm), RNG_STAGE_ENTRIES);
+#pragma unroll 1
+			for (int e0 = 0; e0 < nstage; e0 += 4) {
+				const int e = e0 + g;
+				const bool have = e < nstage;
+				const int T = have ? order_()[e] : 0;
+				const int c = __shfl_sync(full, chunk, T);
+				if (have) {
+					const uint4 *ST = S0 + T * MT_CHUNKS;
+					uint4 *E = stage_() + e * RNG_STAGE_CHUNKS;
+					cp_async16(E + j, ST + mt_wrap(c + j));
+					cp_async16(E + 9 + j, ST + mt_wrap(c + 99 + j));
+					if (j == RNG_GROUP - 1) {
+						cp_async16(E + 8, ST + mt_wrap(c + 8));
+						cp_async16(E + 17, ST + mt_wrap(c + 107));
+					}
+				}
 			}
+			cp_async_commit();
 		}
 		__syncwarp();
 	}
@@ -205,11 +248,7 @@ struct WarpRng {
 		const unsigned full = 0xffffffffu;
 		while (__ballot_sync(full, wants && usable && lvl < need)) {
 			const bool ok = wants && usable;
-			const unsigned room = __ballot_sync(full, ok && lvl <= CAP - RNG_GROUP);
-			// after this refill a served lane holds about lvl+6 pairs and then consumes `need`: who has room next time?
-			const bool served = (room >> lane) & 1u;
-			const unsigned guess = __ballot_sync(full, ok && (served ? lvl + 6 : lvl) - need <= CAP - RNG_GROUP);
-			refill(room, guess);
+			refill(__ballot_sync(full, ok && lvl <= CAP - RNG_GROUP), ok, need);
 		}
 	}
 
@@ -217,8 +256,8 @@ struct WarpRng {
 	__device__ __forceinline__ void pop(double &x1, double &x2, double &r2)
 	{
 		x1 = fx1[rd * RNG_STRIDE + lane];
-		x2 = fx2[rd * RNG_STRIDE + lane];
-		r2 = fr2[rd * RNG_STRIDE + lane];
+		x2 = fx2_()[rd * RNG_STRIDE + lane];
+		r2 = fr2_()[rd * RNG_STRIDE + lane];
 		rd = rd + 1 >= CAP ? 0 : rd + 1;
 		lvl--;
 	}
