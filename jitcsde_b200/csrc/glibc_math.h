@@ -20,8 +20,13 @@
 #if defined(__CUDACC__)
 #define JSDE_FN static __device__ __forceinline__
 #define JSDE_TABLE_QUAL static __device__ const
+// pow runs for one or two lanes of a warp at a time (controller, after a rejection or when the step may grow), so its
+// tables sit in constant memory: few distinct addresses per access, and the lookup does not queue in the load/store
+// unit behind the generator's outstanding asynchronous copies.
+#define JSDE_POWTABLE_QUAL static __constant__ const
 #define JSDE_FMA(a, b, c) __fma_rn((a), (b), (c))
 #define JSDE_TAB(arr, i) __ldg(&(arr)[(i)])
+#define JSDE_PTAB(arr, i) ((arr)[(i)])
 #define JSDE_ASU(x) ((uint64_t)__double_as_longlong(x))
 #define JSDE_ASD(u) __longlong_as_double((long long)(u))
 #else
@@ -31,6 +36,7 @@
 #define JSDE_TABLE_QUAL static const
 #define JSDE_FMA(a, b, c) fma((a), (b), (c))
 #define JSDE_TAB(arr, i) ((arr)[(i)])
+#define JSDE_PTAB(arr, i) ((arr)[(i)])
 static inline uint64_t jsde_asu_(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
 static inline double jsde_asd_(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
 #define JSDE_ASU(x) jsde_asu_(x)
@@ -130,9 +136,9 @@ JSDE_FN double jsde_pow(double x, double y)
 	const uint64_t iz = ix - (tmp & (0xfffULL << 52));
 	const double z = JSDE_ASD(iz);
 	const double kd = (double)k;
-	const double invc = JSDE_TAB(JSDE_POW_INVC, i);
-	const double logc = JSDE_TAB(JSDE_POW_LOGC, i);
-	const double logctail = JSDE_TAB(JSDE_POW_LOGCTAIL, i);
+	const double invc = JSDE_PTAB(JSDE_POW_INVC, i);
+	const double logc = JSDE_PTAB(JSDE_POW_LOGC, i);
+	const double logctail = JSDE_PTAB(JSDE_POW_LOGCTAIL, i);
 	const double t1 = JSDE_FMA(kd, JSDE_LN2HI, logc);
 	const double lo1 = JSDE_FMA(kd, JSDE_LN2LO, logctail);
 	const double r = JSDE_FMA(z, invc, -1.0);
@@ -164,8 +170,8 @@ JSDE_FN double jsde_pow(double x, double y)
 	double rr = JSDE_FMA(kd2, JSDE_EXP_NEGLN2LON, JSDE_FMA(kd2, JSDE_EXP_NEGLN2HIN, ehi));
 	rr = elo + rr;
 	const int idx = 2 * (int)(ki & 127);
-	const double tail = JSDE_ASD(JSDE_TAB(JSDE_EXP_TAB, idx));
-	const uint64_t sbits = JSDE_TAB(JSDE_EXP_TAB, idx + 1) + (ki << 45);
+	const double tail = JSDE_ASD(JSDE_PTAB(JSDE_EXP_TAB, idx));
+	const uint64_t sbits = JSDE_PTAB(JSDE_EXP_TAB, idx + 1) + (ki << 45);
 	const double scale = JSDE_ASD(sbits);
 	const double rr2 = rr * rr;
 	const double q = JSDE_FMA(JSDE_FMA(rr, JSDE_EXP_C3, JSDE_EXP_C2), rr2, rr + tail);

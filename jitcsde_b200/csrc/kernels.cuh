@@ -104,9 +104,13 @@ __global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleVi
 	bool need_target = true, to_jump = false;
 	double tgt = target;
 	while (__any_sync(0xffffffffu, active)) {
-		rng.ensure(active, N);
+		const bool refilled = rng.ensure(active, N);
+		bool attempt = false, last = false;
+		double actual_dt = 0.0;
+		double I1[N], DZ[N];
+		typename Lane<Model>::NoiseScan scan;
 		if (active) {
-			bool attempt = true;
+			attempt = true;
 			if (need_target) {
 				tgt = target;
 				to_jump = false;
@@ -140,43 +144,46 @@ __global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleVi
 				}
 			}
 			if (attempt) {
-				double actual_dt;
-				bool last;
-				if (L.t + L.dt < tgt) {
+				if (L.t + L.dt < tgt)
 					actual_dt = L.dt;
-					last = false;
-				} else {
+				else {
 					actual_dt = tgt - L.t;
 					last = true;
 				}
-				if (!L.propose(actual_dt))
-					active = false;  // noise memory overflow
-				else {
-					const int verdict = L.adjust_step(c, actual_dt);
-					if (verdict == 1) {
-						L.commit();
-						acc++;
-						if (last) {
-							if (!to_jump)
-								active = false;
-							else {
-								double change[N];  // apply_jump(amp(time, state)) (:696-698)
-								Model::jump(L.t, L.y, e.xis[k * e.tape_len + tape_pos], L.par, change);
-#pragma unroll
-								for (int i = 0; i < N; i++)
-									L.y[i] += change[i];
-								tape_pos++;
-								jumps++;
-								jump_set = false;
-								need_target = true;
-							}
-						}
-					} else {
-						rej++;
-						if (verdict < 0) {
-							L.status = TRAJ_MIN_STEP;
+				L.scan_noise(actual_dt, scan, I1, DZ);  // this round's noise-memory loads
+			}
+		}
+		if (refilled)  // warp-uniform: start fetching the next refill's generator words now that our loads are out
+			rng.stage_ahead(active, N);
+		if (attempt) {
+			if (!L.finish_noise(scan, I1, DZ))
+				active = false;  // noise memory overflow
+			else {
+				L.stages(actual_dt, I1, DZ);
+				const int verdict = L.adjust_step(c, actual_dt);
+				if (verdict == 1) {
+					L.commit();
+					acc++;
+					if (last) {
+						if (!to_jump)
 							active = false;
+						else {
+							double change[N];  // apply_jump(amp(time, state)) (:696-698)
+							Model::jump(L.t, L.y, e.xis[k * e.tape_len + tape_pos], L.par, change);
+#pragma unroll
+							for (int i = 0; i < N; i++)
+								L.y[i] += change[i];
+							tape_pos++;
+							jumps++;
+							jump_set = false;
+							need_target = true;
 						}
+					}
+				} else {
+					rej++;
+					if (verdict < 0) {
+						L.status = TRAJ_MIN_STEP;
+						active = false;
 					}
 				}
 			}

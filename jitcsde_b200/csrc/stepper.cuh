@@ -177,93 +177,104 @@ struct Lane {
 	}
 
 	// ---- noise memory -------------------------------------------------------------------------------------------
-	// get_noise (template:204-250).  At most one fresh item is drawn per call: after a bridge or an append the item
-	// at the cursor has exactly the missing length, so the reference's loop consumes it and stops.
-	__device__ __forceinline__ bool collect_noise(double h, double (&W)[N], double (&Z)[N])
+	// get_noise (template:204-250), in two halves so that the kernel can put the generator's asynchronous staging
+	// between the noise memory's loads and everything that follows.  At most one fresh item is drawn per call: after
+	// a bridge or an append the item at the cursor has exactly the missing length, so the reference's loop consumes
+	// it and stops.
+	struct NoiseScan {
+		double need, hq;
+		double qW[N], qZ[N];  // the too-long item at the cursor (valid when cur < count after the scan)
+		int cur;
+		bool started;
+	};
+
+	// first half: consume whole items from the head of the memory
+	__device__ __forceinline__ void scan_noise(double h, NoiseScan &s, double (&W)[N], double (&Z)[N])
 	{
-		bool started = false;
-		double need = h;
-		int cur = 0;
-		double hq = 0.0, qW[N], qZ[N];  // item at the cursor (valid when cur < count)
-		bool have_item = false;
-		while (need != 0.0 && cur < count) {
-			load_item(cur, hq, qW, qZ);
-			have_item = true;
-			if (!(hq <= need))
+		s.started = false;
+		s.need = h;
+		s.cur = 0;
+		s.hq = 0.0;
+		while (s.need != 0.0 && s.cur < count) {
+			load_item(s.cur, s.hq, s.qW, s.qZ);
+			if (!(s.hq <= s.need))
 				break;
-			if (started) {
+			if (s.started) {
 #pragma unroll
 				for (int i = 0; i < N; i++) {
-					W[i] += qW[i];
-					Z[i] += qZ[i];
+					W[i] += s.qW[i];
+					Z[i] += s.qZ[i];
 				}
 			} else {
-				started = true;
+				s.started = true;
 #pragma unroll
 				for (int i = 0; i < N; i++) {
-					W[i] = qW[i];
-					Z[i] = qZ[i];
+					W[i] = s.qW[i];
+					Z[i] = s.qZ[i];
 				}
 			}
-			need -= hq;
-			cur++;
-			have_item = false;
+			s.need -= s.hq;
+			s.cur++;
 		}
-		if (need != 0.0) {
+	}
+
+	// second half: bridge or append with one fresh draw if something is still missing
+	__device__ __forceinline__ bool finish_noise(NoiseScan &s, double (&W)[N], double (&Z)[N])
+	{
+		if (s.need != 0.0) {
 			if (count >= e.D) {
 				status = TRAJ_NOISE_OVERFLOW;
 				return false;
 			}
-			const bool bridging = cur < count;  // then the loop above left the too-long item in (hq, qW, qZ)
+			const bool bridging = s.cur < count;  // then the scan left the too-long item in (hq, qW, qZ)
 			double h_exc = 0.0, factor = 0.0, scale;
 			if (bridging) {  // Brownian_bridge (template:178-202)
-				h_exc = hq - need;
-				factor = h_exc / hq;
-				scale = sqrt(factor * need);
+				h_exc = s.hq - s.need;
+				factor = h_exc / s.hq;
+				scale = sqrt(factor * s.need);
 			} else  // append_noise (template:170-176)
-				scale = sqrt(need);
+				scale = sqrt(s.need);
 			double gW[N], gZ[N];
 			draw(scale, gW, gZ);
 			fresh++;
 			if (bridging) {
 #pragma unroll 1
-				for (int d = count - 1; d > cur; d--)  // make room behind the cursor (the reference relinks its list)
+				for (int d = count - 1; d > s.cur; d--)  // make room behind the cursor (the reference relinks its list)
 					move_item(d + 1, d);
 				double w2[N], z2[N];
 #pragma unroll
 				for (int i = 0; i < N; i++) {
-					w2[i] = gW[i] + qW[i] * factor;
-					z2[i] = gZ[i] + qZ[i] * factor;
-					gW[i] = qW[i] - w2[i];
-					gZ[i] = qZ[i] - z2[i];
+					w2[i] = gW[i] + s.qW[i] * factor;
+					z2[i] = gZ[i] + s.qZ[i] * factor;
+					gW[i] = s.qW[i] - w2[i];
+					gZ[i] = s.qZ[i] - z2[i];
 				}
-				store_item(cur + 1, h_exc, w2, z2);
+				store_item(s.cur + 1, h_exc, w2, z2);
 			}
-			(void)have_item;
-			store_item(cur, need, gW, gZ);
+			store_item(s.cur, s.need, gW, gZ);
 			count++;
-			if (started) {
+			if (s.started) {
 #pragma unroll
 				for (int i = 0; i < N; i++) {
 					W[i] += gW[i];
 					Z[i] += gZ[i];
 				}
 			} else {
-				started = true;
+				s.started = true;
 #pragma unroll
 				for (int i = 0; i < N; i++) {
 					W[i] = gW[i];
 					Z[i] = gZ[i];
 				}
 			}
-			cur++;
+			s.cur++;
 		}
-		if (!started) {
+		if (!s.started) {
 #pragma unroll
 			for (int i = 0; i < N; i++)
 				W[i] = Z[i] = 0.0;
 		}
-		cursor = cur;
+		cursor = s.cur;
 		max_depth = count > max_depth ? count : max_depth;
 		return true;
 	}
@@ -287,9 +298,19 @@ struct Lane {
 	// ---- proposal (get_next_step) ---------------------------------------------------------------------------------
 	__device__ __forceinline__ bool propose(double h)
 	{
-		double I1[N], DZ[N], I10[N];
-		if (!collect_noise(h, I1, DZ))
+		double I1[N], DZ[N];
+		NoiseScan s;
+		scan_noise(h, s, I1, DZ);
+		if (!finish_noise(s, I1, DZ))
 			return false;
+		stages(h, I1, DZ);
+		return true;
+	}
+
+	// the Runge–Kutta stages proper, from the Wiener increments I1 = DW and DZ of this step
+	__device__ __forceinline__ void stages(double h, const double (&I1)[N], const double (&DZ)[N])
+	{
+		double I10[N];
 		double arg[N], fh1[N], fh2[N], g1[N], g2[N];
 		if constexpr (!ADDITIVE) {
 			double g3[N], g4[N];
@@ -352,7 +373,6 @@ struct Lane {
 			}
 		}
 		nt = t + h;
-		return true;
 	}
 
 	// get_p (template:502-526): a 0/0 component is skipped, a NaN never wins the comparison

@@ -100,9 +100,9 @@ struct WarpRng {
 	// ---- cooperative refill ------------------------------------------------------------------------------------------
 	// `room` = lanes whose FIFO can take a full group.  They are served four at a time ("slot": 4 trajectories x 8
 	// candidates), each exactly once, in one run-time loop (unrolled variants blew the 32 KB instruction cache,
-	// profiles/r01_v3_*).  The loop is software-pipelined: the state words of slot s+1 are loaded into registers
-	// before slot s is processed, so only the first slot's load latency is exposed — and that one is usually an L1 hit
-	// because the previous refill ended by prefetching the lines its successor will start with.
+	// profiles/r01_v3_*).  A trajectory's state words normally come from the shared-memory staging area that
+	// stage_ahead() filled one phase earlier with asynchronous copies; trajectories that were not staged (prediction
+	// miss, staging area full, single-step kernels) are read from global memory directly.
 	struct SlotWords {
 		uint4 a, tap;
 		uint32_t edge_next, edge_tap;
@@ -146,7 +146,7 @@ struct WarpRng {
 		return w;
 	}
 
-	__device__ __forceinline__ void refill(unsigned room, bool wants, int need)
+	__device__ __forceinline__ void refill(unsigned room)
 	{
 		const unsigned full = 0xffffffffu;
 		const int g = lane >> 3, j = lane & 7;
@@ -202,12 +202,40 @@ struct WarpRng {
 			if ((below >> 2) == s)
 				mine = __popc((okm >> ((below & 3) * RNG_GROUP)) & 0xffu);
 		}
+		__syncwarp();  // all staged words of this refill have been read
 		if (mine_served) {
 			lvl += mine;
 			chunk = mt_wrap(chunk + RNG_GROUP);
+			stage_of_()[lane] = 0xFF;  // whatever was staged for this trajectory belonged to the position just consumed
 		}
-		// tail: stage the state words of the trajectories that will have room after their next draw (the refill that
-		// follows will serve exactly those) with asynchronous copies, so that their HBM latency overlaps the step phase
+		__syncwarp();
+	}
+
+	// Make sure every lane with `wants` holds at least `need` pairs.  Whole warp must call (convergent).
+	// Everybody with room is served, not only the needy: every slot does useful work as long as it is full.
+	// Returns whether a refill happened (warp-uniform) — the caller then calls stage_ahead() once its own global-memory
+	// loads of this round have been issued.
+	__device__ __forceinline__ bool ensure(bool wants, int need)
+	{
+		const unsigned full = 0xffffffffu;
+		bool refilled = false;
+		while (__ballot_sync(full, wants && usable && lvl < need)) {
+			refill(__ballot_sync(full, wants && usable && lvl <= CAP - RNG_GROUP));
+			refilled = true;
+		}
+		return refilled;
+	}
+
+	// Stage the state words of the trajectories that will have room after their next draw (the next refill will serve
+	// exactly those) with asynchronous copies, so that their HBM latency overlaps the rest of the step phase.  The
+	// load/store unit returns data in order, so anything the warp loads from global or local memory AFTER this call
+	// waits for the copies: call it after the round's noise-memory loads.  Whole warp must call.
+	__device__ __forceinline__ void stage_ahead(bool wants, int need)
+	{
+		const unsigned full = 0xffffffffu;
+		const int g = lane >> 3, j = lane & 7;
+		const unsigned lt = (1u << lane) - 1u;
+		wants = wants && usable;
 		__syncwarp();  // everybody is done reading `order`, `stage_of` and `stage`
 		{
 			const bool will = wants && lvl - need <= CAP - RNG_GROUP;
@@ -237,18 +265,6 @@ struct WarpRng {
 				}
 			}
 			cp_async_commit();
-		}
-		__syncwarp();
-	}
-
-	// Make sure every lane with `wants` holds at least `need` pairs.  Whole warp must call (convergent).
-	// Everybody with room is served, not only the needy: every slot does useful work as long as it is full.
-	__device__ __forceinline__ void ensure(bool wants, int need)
-	{
-		const unsigned full = 0xffffffffu;
-		while (__ballot_sync(full, wants && usable && lvl < need)) {
-			const bool ok = wants && usable;
-			refill(__ballot_sync(full, ok && lvl <= CAP - RNG_GROUP), ok, need);
 		}
 	}
 
