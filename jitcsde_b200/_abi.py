@@ -55,7 +55,7 @@ ABI_SYMBOLS = (
 	"jsde_set_integration_parameters", "jsde_set_parameters", "jsde_pin_noise", "jsde_integrate", "jsde_integrate_jumps",
 	"jsde_get_state", "jsde_get_controller_state", "jsde_moments", "jsde_get_next_step", "jsde_get_p", "jsde_accept_step",
 	"jsde_apply_jump", "jsde_set_time", "jsde_draw_gauss_debug", "jsde_dump_noise", "jsde_measure_fp64_peak",
-	"jsde_debug_log", "jsde_debug_pow", "jsde_last_error", "jsde_version",
+	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_shared_div", "jsde_last_error", "jsde_version",
 )
 
 
@@ -87,6 +87,7 @@ def _declare(lib):
 	lib.jsde_measure_fp64_peak.argtypes = [ctypes.c_int, c_double_p]
 	lib.jsde_debug_log.argtypes = [ctypes.c_int, c_double_p, c_double_p, ctypes.c_int64]
 	lib.jsde_debug_pow.argtypes = [ctypes.c_int, c_double_p, ctypes.c_double, c_double_p, ctypes.c_int64]
+	lib.jsde_debug_shared_div.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, c_u8_p, ctypes.c_int64]
 	for name in ABI_SYMBOLS:
 		fn = getattr(lib, name)
 		if fn.restype is ctypes.c_int and name not in ("jsde_last_error", "jsde_version", "jsde_model_name"):
@@ -301,3 +302,14 @@ def device_pow(lib, x, y, device=0):
 	if lib.jsde_debug_pow(device, _dp(x), float(y), _dp(out), x.size) != 0:
 		raise JsdeError(lib.jsde_last_error().decode())
 	return out
+
+
+def device_shared_div(lib, a, b, device=0):
+	"""(a/b through the stages' shared-divisor path, tame mask)"""
+	a = np.ascontiguousarray(a, dtype=np.float64)
+	b = np.ascontiguousarray(b, dtype=np.float64)
+	out = np.empty_like(a)
+	tame = np.empty(a.size, dtype=np.uint8)
+	if lib.jsde_debug_shared_div(device, _dp(a), _dp(b), _dp(out), tame.ctypes.data_as(c_u8_p), a.size) != 0:
+		raise JsdeError(lib.jsde_last_error().decode())
+	return out, tame.astype(bool)

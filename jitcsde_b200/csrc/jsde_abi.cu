@@ -579,6 +579,31 @@ static int debug_unary(int device, const double *x_host, double *out_host, int64
 	return JSDE_OK;
 }
 
+int jsde_debug_shared_div(int device, const double *a_host, const double *b_host, double *out_host, unsigned char *tame_host, int64_t count)
+{
+	if (!a_host || !b_host || !out_host || !tame_host || count < 0)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	CU(cudaSetDevice(device));
+	double *a = nullptr, *b = nullptr, *o = nullptr;
+	unsigned char *t = nullptr;
+	CU(cudaMalloc(&a, count * sizeof(double) + 16));
+	CU(cudaMalloc(&b, count * sizeof(double) + 16));
+	CU(cudaMalloc(&o, count * sizeof(double) + 16));
+	CU(cudaMalloc(&t, count + 16));
+	cudaError_t err = cudaMemcpy(a, a_host, count * sizeof(double), cudaMemcpyHostToDevice);
+	if (err == cudaSuccess) err = cudaMemcpy(b, b_host, count * sizeof(double), cudaMemcpyHostToDevice);
+	if (err == cudaSuccess) {
+		k_debug_shared_div<<<grid_for(count, 256), 256>>>(a, b, o, t, count);
+		err = cudaGetLastError();
+	}
+	if (err == cudaSuccess) err = cudaMemcpy(out_host, o, count * sizeof(double), cudaMemcpyDeviceToHost);
+	if (err == cudaSuccess) err = cudaMemcpy(tame_host, t, count, cudaMemcpyDeviceToHost);
+	cudaFree(a); cudaFree(b); cudaFree(o); cudaFree(t);
+	if (err != cudaSuccess)
+		return fail(JSDE_E_CUDA, cudaGetErrorString(err));
+	return JSDE_OK;
+}
+
 int jsde_debug_log(int device, const double *x_host, double *out_host, int64_t count) { return debug_unary(device, x_host, out_host, count, 0, 0.0); }
 int jsde_debug_pow(int device, const double *x_host, double y, double *out_host, int64_t count) { return debug_unary(device, x_host, out_host, count, 1, y); }
 

@@ -397,6 +397,18 @@ __global__ void k_debug_log(const double *x, double *out, int64_t count)
 		out[i] = jsde_log(x[i]);
 }
 
+// out[i] = a[i]/b[i] through the shared-divisor path (exact_div.cuh); tame[i] tells whether that path vouches for it
+__global__ void k_debug_shared_div(const double *a, const double *b, double *out, unsigned char *tame, int64_t count)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) {
+		bool ok = true;
+		const SharedDivisor d(b[i]);
+		out[i] = d.divide(a[i], ok);
+		tame[i] = ok ? 1 : 0;
+	}
+}
+
 __global__ void k_debug_pow(const double *x, double yexp, double *out, int64_t count)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

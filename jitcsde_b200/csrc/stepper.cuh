@@ -13,6 +13,7 @@
 #pragma once
 
 #include "ensemble.cuh"
+#include "exact_div.cuh"
 #include "warp_rng.cuh"
 
 namespace jsde {
@@ -307,14 +308,30 @@ struct Lane {
 		return true;
 	}
 
-	// the Runge–Kutta stages proper, from the Wiener increments I1 = DW and DZ of this step
+	// the Runge–Kutta stages proper, from the Wiener increments I1 = DW and DZ of this step.  The quotients by h,
+	// sqrt(h) and 6 go through exact_div.cuh (same bits as `/`, straight-line code); if an operand is outside the range
+	// for which that is proven, the attempt is redone with ordinary divisions.
 	__device__ __forceinline__ void stages(double h, const double (&I1)[N], const double (&DZ)[N])
 	{
+		if (!stages_impl<true>(h, I1, DZ))
+			stages_impl<false>(h, I1, DZ);  // cold: inlined here, never executed for sane step sizes and states
+	}
+
+	template <bool FAST>
+	__device__ __forceinline__ bool stages_impl(double h, const double (&I1)[N], const double (&DZ)[N])
+	{
+		bool tame = true;
+		const SharedDivisor by_h(h);
+		const SharedDivisor by_6(6.0, 1.0 / 6.0);
+		auto div_h = [&](double a) { return FAST ? by_h.divide(a, tame) : a / h; };
+		auto div_6 = [&](double a) { return FAST ? by_6.divide(a, tame) : a / 6; };
 		double I10[N];
 		double arg[N], fh1[N], fh2[N], g1[N], g2[N];
 		if constexpr (!ADDITIVE) {
 			double g3[N], g4[N];
 			const double sqh = sqrt(h);
+			const SharedDivisor by_sqh(sqh);
+			auto div_sqh = [&](double a) { return FAST ? by_sqh.divide(a, tame) : a / sqh; };
 #pragma unroll
 			for (int i = 0; i < N; i++)  // template:289; I_11/sqrt(h) and I_111 (:286-287) are formed where they are used
 				I10[i] = (I1[i] + DZ[i] * (1. / 1.7320508075688772)) * (h / 2.);
@@ -322,7 +339,7 @@ struct Lane {
 			Model::diffusion(t, y, par, g1);
 #pragma unroll
 			for (int i = 0; i < N; i++)
-				arg[i] = y[i] + 0.75 * fh1[i] + 1.5 * g1[i] * I10[i] / h;
+				arg[i] = y[i] + 0.75 * fh1[i] + div_h(1.5 * g1[i] * I10[i]);
 			Model::drift(t + 0.75 * h, arg, h, par, fh2);
 #pragma unroll
 			for (int i = 0; i < N; i++)
@@ -336,11 +353,12 @@ struct Lane {
 			for (int i = 0; i < N; i++)
 				arg[i] = y[i] + 0.25 * fh1[i] + sqh * (-5 * g1[i] + 3 * g2[i] + 0.5 * g3[i]);
 			Model::diffusion(t + 0.25 * h, arg, par, g4);
+			const double third_over_h = 1. / h / 3.;
 #pragma unroll
 			for (int i = 0; i < N; i++) {  // template:447-464
-				const double I11s = (I1[i] * I1[i] - h) * 0.5 / sqh;
+				const double I11s = div_sqh((I1[i] * I1[i] - h) * 0.5);
 				const double I111 = (I1[i] * I1[i] * I1[i] - 3 * h * I1[i]) * (1. / 6.);
-				const double E_N = (1. / h / 3.) * (
+				const double E_N = third_over_h * (
 					+ (6 * I10[i] - 6 * I111) * g1[i]
 					+ (-4 * I10[i] + 5 * I111) * g2[i]
 					+ (-2 * I10[i] - 2 * I111) * g3[i]
@@ -350,7 +368,7 @@ struct Lane {
 					+ (-3 * I1[i] - 3 * I11s) * g1[i]
 					+ (4 * I1[i] + 4 * I11s) * g2[i]
 					+ (2 * I1[i] - I11s) * g3[i]);
-				const double E_D = (fh2[i] - fh1[i]) / 6;
+				const double E_D = div_6(fh2[i] - fh1[i]);
 				er[i] = fabs(E_D) + fabs(E_N);
 			}
 		} else {
@@ -361,18 +379,19 @@ struct Lane {
 			Model::diffusion(t + h, y, par, g1);
 #pragma unroll
 			for (int i = 0; i < N; i++)
-				arg[i] = y[i] + 0.75 * fh1[i] + 0.5 * g1[i] * I10[i] / h;
+				arg[i] = y[i] + 0.75 * fh1[i] + div_h(0.5 * g1[i] * I10[i]);
 			Model::drift(t + 0.75 * h, arg, h, par, fh2);
 			Model::diffusion(t, y, par, g2);
 #pragma unroll
 			for (int i = 0; i < N; i++) {  // template:487-494
-				const double E_N = I10[i] / h * (g2[i] - g1[i]);
+				const double E_N = div_h(I10[i]) * (g2[i] - g1[i]);
 				ny[i] = y[i] + E_N + (1. / 3.) * (fh1[i] + 2 * fh2[i]) + I1[i] * g1[i];
-				const double E_D = (fh2[i] - fh1[i]) / 6;
+				const double E_D = div_6(fh2[i] - fh1[i]);
 				er[i] = fabs(E_D) + fabs(E_N);
 			}
 		}
 		nt = t + h;
+		return tame;
 	}
 
 	// get_p (template:502-526): a 0/0 component is skipped, a NaN never wins the comparison

@@ -55,6 +55,42 @@ def test_device_log_pow_equal_host_libm():
 			assert_bits_equal(_abi.device_pow(lib, x, yexp), ref, "device pow vs libm")
 
 
+def test_shared_divisor_division_is_exact():
+	"""exact_div.cuh: five fused operations + a pre-rounded reciprocal must give the IEEE quotient bit for bit whenever
+	the path calls itself tame, and must decline (not guess) outside its proven range."""
+	lib = _abi.load_library(models.lorenz_additive)
+	rng = np.random.default_rng(11)
+	N = 1 << 24
+	def mant(n):
+		return 1.0 + rng.integers(0, 1 << 52, n, dtype=np.uint64).astype(np.float64) / 2.0 ** 52
+	cases = []
+	for _ in range(4):  # random mantissas, exponents well inside and around the tame range
+		cases.append((mant(N) * 2.0 ** rng.integers(-390, 390, N) * rng.choice([-1.0, 1.0], N), mant(N) * 2.0 ** rng.integers(-390, 390, N)))
+	# divisors the stages really use: step sizes, their square roots, 6; numerators of every magnitude incl. zeros
+	h = 10.0 ** rng.uniform(-10, 1, N)
+	cases.append((rng.standard_normal(N) * 10.0 ** rng.uniform(-12, 3, N), h))
+	cases.append((rng.standard_normal(N), np.sqrt(h)))
+	cases.append((rng.standard_normal(N) * 10.0 ** rng.uniform(-300, 300, N), np.full(N, 6.0)))
+	z = rng.standard_normal(N); z[::3] = 0.0; z[1::3] = -0.0
+	cases.append((z, h))
+	# hard patterns: divisor mantissa all ones / nearly one, quotients near rounding boundaries (a = q*b rounded)
+	b = np.nextafter(2.0, 0.0) * 2.0 ** rng.integers(-50, 50, N)
+	cases.append((mant(N), b))
+	q = mant(N); b2 = mant(N)
+	cases.append((q * b2, b2))
+	cases.append((np.nextafter(q * b2, np.inf), b2))
+	# outside the proven range: must be flagged, whatever the value
+	cases.append((mant(N) * 2.0 ** rng.integers(-1000, -500, N), mant(N)))
+	for a, b in cases:
+		got, tame = _abi.device_shared_div(lib, a, b)
+		with np.errstate(all="ignore"):
+			want = a / b
+		assert_bits_equal(got[tame], want[tame], "shared-divisor quotient")
+	assert not tame.any()  # the last case lies outside the tame range entirely
+	got, tame = _abi.device_shared_div(lib, np.array([1.0, np.inf, np.nan, 1e300, 0.0]), np.array([1e-320, 2.0, 2.0, 1e-300, 3.0]))
+	assert list(tame) == [False, False, False, False, True] and got[4] == 0.0
+
+
 # ---- Gaussian stream --------------------------------------------------------------------------------------------------
 def test_gauss_stream_bit_exact_many_seeds():
 	"""rk_gauss pairs per trajectory == oracle, across several regenerations of the 624-word block."""
