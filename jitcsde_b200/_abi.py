@@ -52,7 +52,7 @@ class JumpTape(ctypes.Structure):
 #: every symbol include/jsde.h declares (tests/test_abi_symbols.py checks the built library exports them all)
 ABI_SYMBOLS = (
 	"jsde_model_info", "jsde_model_name", "jsde_create", "jsde_destroy", "jsde_set_state", "jsde_seed",
-	"jsde_set_integration_parameters", "jsde_set_parameters", "jsde_pin_noise", "jsde_integrate", "jsde_integrate_jumps",
+	"jsde_set_integration_parameters", "jsde_set_parameters", "jsde_pin_noise", "jsde_integrate", "jsde_integrate_jumps", "jsde_integrate_grid",
 	"jsde_get_state", "jsde_get_controller_state", "jsde_moments", "jsde_get_next_step", "jsde_get_p", "jsde_accept_step",
 	"jsde_apply_jump", "jsde_set_time", "jsde_draw_gauss_debug", "jsde_dump_noise", "jsde_measure_fp64_peak",
 	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_shared_div", "jsde_last_error", "jsde_version",
@@ -74,6 +74,7 @@ def _declare(lib):
 	lib.jsde_pin_noise.argtypes = [H, ctypes.c_uint, ctypes.c_double]
 	lib.jsde_integrate.argtypes = [H, ctypes.c_double, ctypes.POINTER(Stats)]
 	lib.jsde_integrate_jumps.argtypes = [H, ctypes.c_double, ctypes.POINTER(JumpTape), ctypes.POINTER(Stats)]
+	lib.jsde_integrate_grid.argtypes = [H, c_double_p, ctypes.c_int64, ctypes.POINTER(JumpTape), c_double_p, ctypes.POINTER(Stats)]
 	lib.jsde_get_state.argtypes = [H, c_double_p, c_double_p, c_i32_p]
 	lib.jsde_get_controller_state.argtypes = [H, c_double_p, c_u64_p, c_u64_p]
 	lib.jsde_moments.argtypes = [H, ctypes.c_void_p, c_double_p]
@@ -210,6 +211,22 @@ class Ensemble:
 		self._check(self.lib.jsde_integrate_jumps(self._h, float(target_time), ctypes.byref(self._tape[3]), ctypes.byref(st)))
 		self.last_stats = st.as_dict()
 		return self.last_stats
+
+	def integrate_grid(self, times, taus=None, xis=None):
+		"""States at every sample time, [n_times][B][n], from ONE launch (semantics of consecutive integrate() calls)."""
+		times = np.ascontiguousarray(times, dtype=np.float64)
+		out = np.zeros((times.size, self.B, self.n))
+		tape = None
+		if taus is not None:
+			if self._tape is None or self._tape[0] is not taus:
+				t = np.ascontiguousarray(taus, dtype=np.float64)
+				x = np.ascontiguousarray(xis, dtype=np.float64)
+				self._tape = (taus, t, x, JumpTape(_dp(t), _dp(x), t.shape[1]))
+			tape = ctypes.byref(self._tape[3])
+		st = Stats()
+		self._check(self.lib.jsde_integrate_grid(self._h, _dp(times), times.size, tape, _dp(out), ctypes.byref(st)))
+		self.last_stats = st.as_dict()
+		return out
 
 	# ---- results -------------------------------------------------------------------------------------------------------
 	def get_state(self, out=None):

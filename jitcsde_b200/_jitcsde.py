@@ -289,6 +289,18 @@ class jitcsde:
 		self._raise_on_failure(stats)
 		return self._shape_out(self.SDE.get_state())
 
+	def integrate_grid(self, times):
+		"""
+		`[self.integrate(T) for T in times]` in one kernel launch: ndarray [len(times)][B][n] (or [len(times)][n] for an
+		ensemble of one).  Same results bit for bit as the loop of calls the reference's examples use
+		(`examples/noisy_lorenz.py:95-96`), without one launch and one host round trip per sample.
+		"""
+		self._initiate()
+		out = self.SDE.integrate_grid(times)
+		self.last_stats = self.SDE.last_stats
+		self._raise_on_failure(self.last_stats)
+		return out[:, 0, :] if self.B == 1 else out
+
 	def pin_noise(self, number, step_size):
 		"""reference `_jitcsde.py:632-654`"""
 		self._initiate()

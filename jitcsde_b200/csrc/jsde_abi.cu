@@ -206,7 +206,8 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 		return bail(fail(JSDE_E_CUDA, cudaGetErrorString(err)));
 	// the generator FIFOs + staging area exceed the 48 KB default for dynamic shared memory
 	const int smem = (int)rng_smem_bytes<Model>();
-	if ((err = cudaFuncSetAttribute(k_integrate<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+	if ((err = cudaFuncSetAttribute(k_integrate<Model, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+		(err = cudaFuncSetAttribute(k_integrate<Model, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
 		(err = cudaFuncSetAttribute(k_get_next_step<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
 		(err = cudaFuncSetAttribute(k_pin_noise<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
 		(err = cudaFuncSetAttribute(k_draw_gauss<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
@@ -325,15 +326,80 @@ int jsde_pin_noise(jsde_t *h, unsigned number, double step)
 	return JSDE_OK;
 }
 
-static int integrate_common(jsde_t *h, double target_time, int use_tape, jsde_stats *stats_host)
+static int integrate_common(jsde_t *h, double target_time, int use_tape, jsde_stats *stats_host,
+	const double *grid_times_dev = nullptr, int grid_count = 0, double *grid_out_dev = nullptr)
 {
 	if (!(target_time == target_time))
 		return fail(JSDE_E_ARG, "Wrong input. (target time is NaN)");
 	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
 	CU(cudaEventRecord(h->ev0, h->stream));
-	k_integrate<Model><<<grid_for(h->B, BLOCK), BLOCK, rng_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape);
+	if (grid_times_dev)
+		k_integrate<Model, true><<<grid_for(h->B, BLOCK), BLOCK, rng_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
+			grid_times_dev, grid_count, grid_out_dev);
+	else
+		k_integrate<Model, false><<<grid_for(h->B, BLOCK), BLOCK, rng_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
+			nullptr, 0, nullptr);
 	CU(cudaGetLastError());
 	return finish_call(h, stats_host, 1);
+}
+
+int jsde_integrate_grid(jsde_t *h, const double *times_host, int64_t n_times, const jsde_jump_tape *tape, double *y_host, jsde_stats *stats_host)
+{
+	if (!h || !times_host || n_times <= 0 || n_times > 0x7fffffff || !y_host)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	for (int64_t j = 0; j < n_times; j++)
+		if (!(times_host[j] == times_host[j]))
+			return fail(JSDE_E_ARG, "Wrong input. (sample time is NaN)");
+	if (tape && !Model::HAS_JUMP)
+		return fail(JSDE_E_STATE, "this model was generated without a jump amplitude");
+	int rc = bind(h);
+	if (rc) return rc;
+	constexpr int n = Model::N;
+	const size_t count = (size_t)n_times * n * (size_t)h->B;
+	double *times = nullptr, *cols = nullptr, *rows = nullptr;
+	CU(cudaMalloc(&times, n_times * sizeof(double)));
+	cudaError_t err = cudaMalloc(&cols, count * sizeof(double));
+	if (err == cudaSuccess) err = cudaMalloc(&rows, (size_t)n * h->B * sizeof(double));
+	if (err != cudaSuccess) {
+		cudaFree(times); cudaFree(cols);
+		return fail(JSDE_E_NOMEM, "sampling grid does not fit in device memory: n_times*n*B doubles");
+	}
+	auto cleanup = [&]() { cudaFree(times); cudaFree(cols); cudaFree(rows); };
+	if ((err = cudaMemcpyAsync(times, times_host, n_times * sizeof(double), cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) {
+		cleanup();
+		return fail(JSDE_E_CUDA, cudaGetErrorString(err));
+	}
+	int use_tape = 0;
+	if (tape) {
+		jsde_stats dummy;
+		// upload / reuse the tape exactly like jsde_integrate_jumps does, without integrating: target = -inf is a no-op
+		(void)dummy;
+		if (tape->taus_host != h->tape_src_taus || tape->xis_host != h->tape_src_xis || tape->length != h->tape_len) {
+			const size_t tcount = (size_t)h->B * (size_t)tape->length;
+			if ((rc = dev_alloc(h, &h->taus, tcount)) || (rc = dev_alloc(h, &h->xis, tcount))) { cleanup(); return rc; }
+			cudaMemcpyAsync(h->taus, tape->taus_host, tcount * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+			cudaMemcpyAsync(h->xis, tape->xis_host, tcount * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+			h->tape_src_taus = tape->taus_host;
+			h->tape_src_xis = tape->xis_host;
+			h->tape_len = tape->length;
+			h->v.taus = h->taus;
+			h->v.xis = h->xis;
+			h->v.tape_len = tape->length;
+		}
+		use_tape = 1;
+	}
+	rc = integrate_common(h, times_host[0], use_tape, stats_host, times, (int)n_times, cols);
+	if (rc == JSDE_OK) {
+		// device layout [n_times][n][B] -> host layout [n_times][B][n], one sample time at a time
+		for (int64_t j = 0; j < n_times && err == cudaSuccess; j++) {
+			k_cols_to_rows<<<grid_for(h->B * n, 256), 256, 0, h->stream>>>(cols + (size_t)j * n * h->B, rows, h->B, n);
+			err = cudaMemcpyAsync(y_host + (size_t)j * n * h->B, rows, (size_t)n * h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+		}
+		if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
+		if (err != cudaSuccess) rc = fail(JSDE_E_CUDA, cudaGetErrorString(err));
+	}
+	cleanup();
+	return rc;
 }
 
 int jsde_integrate(jsde_t *h, double target_time, jsde_stats *stats_host)

@@ -74,9 +74,17 @@ __device__ __forceinline__ WarpRng<Model::N> make_rng(const EnsembleView &e, int
 // The warp alternates between (a) cooperative generator refills until every lane that still has work holds the N
 // pairs an attempt may need and (b) one attempted step per such lane.  Choosing the next target and applying a jump
 // are folded into the same loop so that lanes which jump do not serialise the warp.
-template <class Model>
-__global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleView e, Controller c, double target, int use_tape)
+template <class Model, bool GRID>
+__global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleView e, Controller c, double target, int use_tape,
+	const double *__restrict__ grid_times_, int grid_count, double *__restrict__ grid_out)
 {
+	const double *grid_times = GRID ? grid_times_ : nullptr;  // compile-time nullptr keeps the plain kernel free of grid code
+	// Sampling-grid mode (grid_times != nullptr): the lane integrates to grid_times[0], records its state in
+	// grid_out[0][·][k], goes on to grid_times[1], … — exactly the sequence of integrate() calls of
+	// examples/noisy_lorenz.py:95-96 (truncated last step + Brownian bridge at every sample time), in one launch.
+	int grid_index = 0;
+	if (grid_times)
+		target = grid_times[0];
 	constexpr int N = Model::N;
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	const bool live = k < e.B;
@@ -128,9 +136,19 @@ __global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleVi
 				need_target = false;
 				if (L.t >= tgt) {  // integrate() with nothing to do (:614)
 					attempt = false;
-					if (!to_jump)
+					if (!to_jump) {
 						active = false;
-					else {
+						if (grid_times) {  // next sample time (cold path: once per sample, not per step)
+#pragma unroll
+							for (int i = 0; i < N; i++)
+								grid_out[((int64_t)grid_index * N + i) * e.B + k] = L.y[i];
+							if (++grid_index < grid_count) {
+								target = grid_times[grid_index];
+								need_target = true;
+								active = true;
+							}
+						}
+					} else {
 						double change[N];
 						Model::jump(L.t, L.y, e.xis[k * e.tape_len + tape_pos], L.par, change);
 #pragma unroll
@@ -165,9 +183,19 @@ __global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleVi
 					L.commit();
 					acc++;
 					if (last) {
-						if (!to_jump)
+						if (!to_jump) {
 							active = false;
-						else {
+							if (grid_times) {
+#pragma unroll
+								for (int i = 0; i < N; i++)
+									grid_out[((int64_t)grid_index * N + i) * e.B + k] = L.y[i];
+								if (++grid_index < grid_count) {
+									target = grid_times[grid_index];
+									need_target = true;
+									active = true;
+								}
+							}
+						} else {
 							double change[N];  // apply_jump(amp(time, state)) (:696-698)
 							Model::jump(L.t, L.y, e.xis[k * e.tape_len + tape_pos], L.par, change);
 #pragma unroll

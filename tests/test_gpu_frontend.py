@@ -30,6 +30,21 @@ def test_single_trajectory_like_the_reference_example():
 	assert SDE.t == P.t and SDE.dt == P.dt
 
 
+def test_integrate_grid_equals_the_loop_of_calls():
+	SDE = jitcsde(f, g, verbose=False)
+	SDE.set_seed(42)
+	SDE.set_initial_value(y0, 0.0)
+	times = np.arange(0.0, 0.3, 0.01)
+	data = SDE.integrate_grid(times)
+	assert data.shape == (30, 3)
+	P = port.PortCore(SDE.spec, y0, 0.0, 42)
+	assert_bits_equal(data, np.array([P.integrate(T) for T in times]), "time series")
+	ens = jitcsde(f, g, ensemble=5, verbose=False)
+	ens.set_seed(42)
+	ens.set_initial_value(y0, 0.0)
+	assert_bits_equal(ens.integrate_grid(times)[:, 0, :], data, "ensemble member 0")
+
+
 def test_ensemble_seeding_rule_and_reset():
 	B = 40
 	SDE = jitcsde(f, g, ensemble=B, verbose=False)

@@ -186,6 +186,34 @@ def test_sampled_golden(case):
 	assert [int(a) for a in rej] == [r["rejected"] for r in rec["rows"]]
 
 
+@pytest.mark.parametrize("case", range(len(G["sampled"])))
+def test_sampling_grid_in_one_launch_golden(case):
+	"""jsde_integrate_grid == the same sequence of integrate() calls (golden from the reference core), one launch."""
+	rec = G["sampled"][case]
+	spec = models.ALL[rec["model"]]
+	E, y0, seeds = make(spec, rec["B"])
+	times = unhex(rec["times"])
+	ys = E.integrate_grid(times)  # [time][B][n]
+	for k, row in enumerate(rec["rows"]):
+		assert_bits_equal(ys[:, k, :], unhex(row["ys"]), f"trajectory {k}")
+	_, acc, rej = E.controller_state()
+	assert [int(a) for a in acc] == [r["accepted"] for r in rec["rows"]]
+	assert E.last_stats["kernel_launches"] == 1
+	assert_bits_equal(E.get_state(), ys[-1], "final state")
+
+
+def test_sampling_grid_with_jumps_equals_repeated_calls():
+	spec = models.lorenz_jumpy
+	B = 64
+	taus, xis = jump_tape(B, 16)
+	times = np.linspace(0.0, 2.0, 21)
+	E, y0, seeds = make(spec, B)
+	grid = E.integrate_grid(times, taus, xis)
+	E2, _, _ = make(spec, B)
+	loop = np.array([(E2.integrate_jumps(T, taus, xis), E2.get_state())[1] for T in times])
+	assert_bits_equal(grid, loop, "grid vs loop of calls")
+
+
 def test_jump_golden():
 	rec = G["jumps"][0]
 	spec = models.ALL[rec["model"]]
