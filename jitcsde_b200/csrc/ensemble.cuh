@@ -24,6 +24,8 @@ namespace jsde {
 
 __host__ __device__ constexpr int noise_item_doubles(int n) { return (1 + 2 * n + 1) & ~1; }
 
+enum { TRAJ_OK = 0, TRAJ_MIN_STEP = 1, TRAJ_NOISE_OVERFLOW = 2 };
+
 struct Controller {
 	double atol, rtol, min_step, max_step, dec_thr, inc_thr, safety, max_factor, min_factor;
 	double shrink_exp;  // -1/q        (_jitcsde.py:587)

@@ -484,7 +484,7 @@ int jsde_moments(jsde_t *h, double *acc_dev, const double *shift_host)
 	const int threads = 256;
 	unsigned blocks = grid_for(h->B, threads);
 	if (blocks > 148 * 4) blocks = 148 * 4;
-	k_moments<<<blocks, threads, (threads / 32) * (1 + 2 * n) * sizeof(double), h->stream>>>(h->v.y, h->v.status, h->B, n, h->shift, acc_dev);
+	k_moments<<<blocks, threads, (threads / 32) * (1 + 2 * n) * sizeof(double), h->stream>>>(h->v.y, h->v.status, h->B, n, h->shift, acc_dev, h->B, 1);
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(h->stream));
 	return JSDE_OK;

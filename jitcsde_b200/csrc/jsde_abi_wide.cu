@@ -1,0 +1,356 @@
+// extern "C" boundary (include/jsde.h) for WIDE models (one thread block per trajectory, wide.cuh).  Same ABI as
+// jsde_abi.cu; the entry points the wide path does not implement yet (single-step surface, jumps, sampling grid,
+// pin_noise) return JSDE_E_STATE with a message instead of pretending.  Must be compiled with -fmad=false.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jsde.h"
+#include "glibc_math.h"
+#include "wide.cuh"
+#include "kernels_common.cuh"
+
+#ifndef JSDE_MODEL_HEADER
+#error "compile with -DJSDE_MODEL_HEADER=\"model.cuh\""
+#endif
+#include JSDE_MODEL_HEADER
+
+using jsde_model::Model;
+using namespace jsde;
+using namespace jsde::wide;
+
+static_assert(Model::WIDE, "jsde_abi_wide.cu is for wide models");
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string &msg)
+{
+	g_error = msg;
+	return code;
+}
+
+#define CU(call)                                                                                          \
+	do {                                                                                                  \
+		cudaError_t err__ = (call);                                                                       \
+		if (err__ != cudaSuccess)                                                                         \
+			return fail(err__ == cudaErrorMemoryAllocation ? JSDE_E_NOMEM : JSDE_E_CUDA,                  \
+				std::string(#call) + ": " + cudaGetErrorString(err__));                                   \
+	} while (0)
+
+inline unsigned grid_for(int64_t count, int block) { return (unsigned)((count + block - 1) / block); }
+
+int unsupported(const char *what)
+{
+	return fail(JSDE_E_STATE, std::string(what) + " is not implemented for wide (block-per-trajectory) models yet");
+}
+
+}  // namespace
+
+struct jsde_handle {
+	int device = 0;
+	int64_t B = 0;
+	int D = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	WideView v{};
+	Controller ctrl{};
+	double first_step = 1.0;
+	uint32_t *seeds = nullptr;
+	double *par = nullptr, *shift = nullptr;
+	std::vector<void *> allocations;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(jsde_handle *h, T **ptr, size_t count)
+{
+	void *p = nullptr;
+	CU(cudaMalloc(&p, count * sizeof(T) > 0 ? count * sizeof(T) : 16));
+	h->allocations.push_back(p);
+	*ptr = static_cast<T *>(p);
+	return JSDE_OK;
+}
+
+int bind(jsde_handle *h)
+{
+	CU(cudaSetDevice(h->device));
+	return JSDE_OK;
+}
+
+int reset_integrator(jsde_handle *h)
+{
+	const int64_t B = h->B;
+	CU(cudaMemsetAsync(h->v.q_count, 0, B * sizeof(int), h->stream));
+	CU(cudaMemsetAsync(h->v.status, 0, B * sizeof(int), h->stream));
+	CU(cudaMemsetAsync(h->v.accepted, 0, B * sizeof(unsigned long long), h->stream));
+	CU(cudaMemsetAsync(h->v.rejected, 0, B * sizeof(unsigned long long), h->stream));
+	k_iota_rows<<<grid_for(B * h->D, 256), 256, 0, h->stream>>>(h->v.order, B, h->D);
+	k_wide_seed<<<grid_for(B, 64), 64, 0, h->stream>>>(h->v.key, h->v.fifo_rd, h->v.fifo_cnt, h->seeds, B);
+	CU(cudaGetLastError());
+	return JSDE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *jsde_last_error(void) { return g_error.c_str(); }
+const char *jsde_version(void) { return "jsde-b200 0.1 wide (sm_100a, fp64, -fmad=false)"; }
+const char *jsde_model_name(void) { return JSDE_MODEL_NAME; }
+
+int jsde_model_info(int *n, int *additive, int *n_params, int *has_jump)
+{
+	if (n) *n = Model::N;
+	if (additive) *additive = 1;
+	if (n_params) *n_params = Model::NPAR;
+	if (has_jump) *has_jump = 0;
+	return JSDE_OK;
+}
+
+int jsde_destroy(jsde_t *h)
+{
+	if (!h)
+		return JSDE_OK;
+	cudaSetDevice(h->device);
+	if (h->stream) cudaStreamSynchronize(h->stream);
+	for (void *p : h->allocations) cudaFree(p);
+	if (h->ev0) cudaEventDestroy(h->ev0);
+	if (h->ev1) cudaEventDestroy(h->ev1);
+	if (h->stream) cudaStreamDestroy(h->stream);
+	delete h;
+	return JSDE_OK;
+}
+
+int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
+{
+	if (!out || B <= 0 || noise_capacity < 0 || noise_capacity > MAX_DEPTH)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int count = 0;
+	cudaError_t err = cudaGetDeviceCount(&count);
+	if (err != cudaSuccess || count == 0)
+		return fail(JSDE_E_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(err));
+	if (device < 0 || device >= count)
+		return fail(JSDE_E_ARG, "Wrong input. (device index out of range)");
+	jsde_handle *h = new jsde_handle();
+	h->device = device;
+	h->B = B;
+	h->D = noise_capacity ? noise_capacity : 32;
+	if (h->D < 2) h->D = 2;
+	constexpr int n = Model::N;
+	int rc = bind(h);
+	auto bail = [&](int code) { jsde_destroy(h); return code; };
+	if (rc) return bail(rc);
+	if ((err = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+		(err = cudaEventCreate(&h->ev0)) != cudaSuccess || (err = cudaEventCreate(&h->ev1)) != cudaSuccess)
+		return bail(fail(JSDE_E_CUDA, cudaGetErrorString(err)));
+	WideView &v = h->v;
+	v.B = B;
+	v.D = h->D;
+#define ALLOC(ptr, cnt) if ((rc = dev_alloc(h, &(ptr), (size_t)(cnt)))) return bail(rc)
+	ALLOC(v.y, B * n); ALLOC(v.t, B); ALLOC(v.dt, B);
+	ALLOC(v.qh, B * h->D); ALLOC(v.qw, B * h->D * 2 * n); ALLOC(v.order, B * h->D); ALLOC(v.q_count, B);
+	ALLOC(v.key, B * MT_WORDS); ALLOC(v.fifo, B * 3 * CANDIDATES); ALLOC(v.fifo_rd, B); ALLOC(v.fifo_cnt, B);
+	ALLOC(v.status, B); ALLOC(v.accepted, B); ALLOC(v.rejected, B); ALLOC(v.totals, 1);
+	ALLOC(h->seeds, B); ALLOC(h->par, Model::NPAR > 0 ? Model::NPAR : 1); ALLOC(h->shift, n);
+#undef ALLOC
+	v.par = h->par;
+	Controller &c = h->ctrl;  // defaults of set_integration_parameters (_jitcsde.py:491-502), q = 1.5 (:564)
+	c.atol = 1e-10; c.rtol = 1e-5; c.min_step = 1e-10; c.max_step = 10.0; c.dec_thr = 1.1; c.inc_thr = 0.5;
+	c.safety = 0.9; c.max_factor = 5.0; c.min_factor = 0.2; c.shrink_exp = -1 / 1.5; c.grow_exp = -1 / (1.5 + 1);
+	if ((err = cudaMemsetAsync(h->seeds, 0, B * sizeof(uint32_t), h->stream)) != cudaSuccess ||
+		(err = cudaMemsetAsync(v.y, 0, (size_t)B * n * sizeof(double), h->stream)) != cudaSuccess ||
+		(err = cudaMemsetAsync(v.t, 0, B * sizeof(double), h->stream)) != cudaSuccess ||
+		(err = cudaMemsetAsync(v.qh, 0, (size_t)B * h->D * sizeof(double), h->stream)) != cudaSuccess ||
+		(err = cudaMemsetAsync(h->par, 0, (Model::NPAR > 0 ? Model::NPAR : 1) * sizeof(double), h->stream)) != cudaSuccess)
+		return bail(fail(JSDE_E_CUDA, cudaGetErrorString(err)));
+	k_fill<<<grid_for(B, 256), 256, 0, h->stream>>>(v.dt, h->first_step, B);
+	if ((rc = reset_integrator(h))) return bail(rc);
+	if ((err = cudaStreamSynchronize(h->stream)) != cudaSuccess)
+		return bail(fail(JSDE_E_CUDA, cudaGetErrorString(err)));
+	*out = h;
+	return JSDE_OK;
+}
+
+int jsde_set_state(jsde_t *h, const double *y0_host, const double *t0_host, double t0)
+{
+	if (!h || !y0_host)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc = bind(h);
+	if (rc) return rc;
+	CU(cudaMemcpyAsync(h->v.y, y0_host, (size_t)h->B * Model::N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	if (t0_host)
+		CU(cudaMemcpyAsync(h->v.t, t0_host, h->B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	else
+		k_fill<<<grid_for(h->B, 256), 256, 0, h->stream>>>(h->v.t, t0, h->B);
+	if ((rc = reset_integrator(h))) return rc;
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_seed(jsde_t *h, const uint32_t *seeds_host)
+{
+	if (!h || !seeds_host)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc = bind(h);
+	if (rc) return rc;
+	CU(cudaMemcpyAsync(h->seeds, seeds_host, h->B * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+	if ((rc = reset_integrator(h))) return rc;
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_set_integration_parameters(jsde_t *h, const jsde_ctrl *p)
+{
+	if (!h || !p)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	if (!(p->decrease_threshold >= 1.0) || !(p->increase_threshold <= 1.0) || !(p->max_factor >= 1.0) || !(p->min_factor <= 1.0) ||
+		!(p->safety_factor <= 1.0) || !(p->atol >= 0.0) || !(p->rtol >= 0.0) || !(p->q > 0.0))
+		return fail(JSDE_E_ARG, "Wrong input. (integration parameter out of range)");
+	int rc = bind(h);
+	if (rc) return rc;
+	double first = p->first_step, min_step = p->min_step;
+	if (first > p->max_step) first = p->max_step;  // _jitcsde.py:536-541
+	if (min_step > first) min_step = first;
+	Controller &c = h->ctrl;
+	c.atol = p->atol; c.rtol = p->rtol; c.min_step = min_step; c.max_step = p->max_step;
+	c.dec_thr = p->decrease_threshold; c.inc_thr = p->increase_threshold; c.safety = p->safety_factor;
+	c.max_factor = p->max_factor; c.min_factor = p->min_factor;
+	c.shrink_exp = -1 / p->q;
+	c.grow_exp = -1 / (p->q + 1);
+	h->first_step = first;
+	k_fill<<<grid_for(h->B, 256), 256, 0, h->stream>>>(h->v.dt, first, h->B);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_set_parameters(jsde_t *h, const double *params_host, int per_trajectory)
+{
+	if (!h || (Model::NPAR > 0 && !params_host))
+		return fail(JSDE_E_ARG, "Wrong input.");
+	if (per_trajectory)
+		return unsupported("per-trajectory control parameters");
+	if (Model::NPAR == 0)
+		return JSDE_OK;
+	int rc = bind(h);
+	if (rc) return rc;
+	CU(cudaMemcpyAsync(h->par, params_host, Model::NPAR * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_integrate(jsde_t *h, double target_time, jsde_stats *stats_host)
+{
+	if (!h || !(target_time == target_time))
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc = bind(h);
+	if (rc) return rc;
+	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
+	CU(cudaEventRecord(h->ev0, h->stream));
+	k_wide_integrate<Model><<<(unsigned)h->B, WBLOCK, 0, h->stream>>>(h->v, h->ctrl, target_time);
+	CU(cudaGetLastError());
+	CallTotals tot;
+	CU(cudaEventRecord(h->ev1, h->stream));
+	CU(cudaMemcpyAsync(&tot, h->v.totals, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	if (stats_host) {
+		float ms = 0.f;
+		CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+		stats_host->accepted = tot.accepted;
+		stats_host->rejected = tot.rejected;
+		stats_host->fresh_draws = tot.fresh_draws;
+		stats_host->jumps = 0;
+		stats_host->n_min_step = tot.n_min_step;
+		stats_host->n_overflow = tot.n_overflow;
+		stats_host->max_noise_depth = tot.max_depth;
+		stats_host->kernel_launches = 1;
+		stats_host->kernel_ms = ms;
+	}
+	return JSDE_OK;
+}
+
+int jsde_get_state(jsde_t *h, double *y_host, double *t_host, int32_t *status_host)
+{
+	if (!h)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc = bind(h);
+	if (rc) return rc;
+	if (y_host) CU(cudaMemcpyAsync(y_host, h->v.y, (size_t)h->B * Model::N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	if (t_host) CU(cudaMemcpyAsync(t_host, h->v.t, h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	if (status_host) CU(cudaMemcpyAsync(status_host, h->v.status, h->B * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_get_controller_state(jsde_t *h, double *dt_host, uint64_t *accepted_host, uint64_t *rejected_host)
+{
+	if (!h)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc = bind(h);
+	if (rc) return rc;
+	if (dt_host) CU(cudaMemcpyAsync(dt_host, h->v.dt, h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	if (accepted_host) CU(cudaMemcpyAsync(accepted_host, h->v.accepted, h->B * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+	if (rejected_host) CU(cudaMemcpyAsync(rejected_host, h->v.rejected, h->B * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_moments(jsde_t *h, double *acc_dev, const double *shift_host)
+{
+	if (!h || !acc_dev)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc = bind(h);
+	if (rc) return rc;
+	constexpr int n = Model::N;
+	if (shift_host)
+		CU(cudaMemcpyAsync(h->shift, shift_host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	else
+		CU(cudaMemsetAsync(h->shift, 0, n * sizeof(double), h->stream));
+	CU(cudaMemsetAsync(acc_dev, 0, (1 + 2 * n) * sizeof(double), h->stream));
+	const int threads = 256;
+	unsigned blocks = grid_for(h->B, threads);
+	if (blocks > 148) blocks = 148;
+	k_moments<<<blocks, threads, (threads / 32) * (1 + 2 * n) * sizeof(double), h->stream>>>(h->v.y, h->v.status, h->B, n, h->shift, acc_dev, 1, n);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_set_time(jsde_t *h, const double *t_host)
+{
+	if (!h || !t_host)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc = bind(h);
+	if (rc) return rc;
+	CU(cudaMemcpyAsync(h->v.t, t_host, h->B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_pin_noise(jsde_t *, unsigned, double) { return unsupported("pin_noise"); }
+int jsde_integrate_jumps(jsde_t *, double, const jsde_jump_tape *, jsde_stats *) { return unsupported("jumps"); }
+int jsde_integrate_grid(jsde_t *, const double *, int64_t, const jsde_jump_tape *, double *, jsde_stats *) { return unsupported("the sampling grid"); }
+int jsde_get_next_step(jsde_t *, const double *) { return unsupported("the single-step surface"); }
+int jsde_get_p(jsde_t *, double, double, double *) { return unsupported("the single-step surface"); }
+int jsde_accept_step(jsde_t *, const uint8_t *) { return unsupported("the single-step surface"); }
+int jsde_apply_jump(jsde_t *, const double *) { return unsupported("apply_jump"); }
+int jsde_draw_gauss_debug(jsde_t *, double, int, double *) { return unsupported("the generator debug stream"); }
+int jsde_dump_noise(jsde_t *, int64_t, double *, int, int *) { return unsupported("dump_noise"); }
+int jsde_debug_log(int, const double *, double *, int64_t) { return unsupported("debug_log"); }
+int jsde_debug_pow(int, const double *, double, double *, int64_t) { return unsupported("debug_pow"); }
+int jsde_debug_shared_div(int, const double *, const double *, double *, unsigned char *, int64_t) { return unsupported("debug_shared_div"); }
+
+int jsde_measure_fp64_peak(int device, double *tflops)
+{
+	(void)device;
+	if (tflops) *tflops = 0.0;
+	return unsupported("measure_fp64_peak (use a lane-model library)");
+}
+
+}  // extern "C"

@@ -3,6 +3,7 @@
 #pragma once
 
 #include "stepper.cuh"
+#include "kernels_common.cuh"
 
 namespace jsde {
 
@@ -327,121 +328,6 @@ __global__ void __launch_bounds__(BLOCK) k_draw_gauss(EnsembleView e, double sca
 		}
 	}
 	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
-}
-
-// ---- model-independent helpers ------------------------------------------------------------------------------------
-__global__ void k_seed(uint4 *mt, int *mt_chunk, const uint32_t *seeds, int64_t B)
-{
-	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= B)
-		return;
-	mt_seed(mt + k * MT_CHUNKS, seeds[k]);
-	mt_chunk[k] = 0;
-}
-
-// rows [B][n] (trajectory-major, host layout)  <->  cols [n][B] (device layout)
-__global__ void k_rows_to_cols(const double *rows, double *cols, int64_t B, int n, int accumulate)
-{
-	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= B * n)
-		return;
-	const int64_t k = idx / n;
-	const int i = (int)(idx - k * n);
-	if (accumulate)
-		cols[(int64_t)i * B + k] += rows[idx];
-	else
-		cols[(int64_t)i * B + k] = rows[idx];
-}
-
-__global__ void k_cols_to_rows(const double *cols, double *rows, int64_t B, int n)
-{
-	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= B * n)
-		return;
-	const int64_t k = idx / n;
-	const int i = (int)(idx - k * n);
-	rows[idx] = cols[(int64_t)i * B + k];
-}
-
-__global__ void k_fill(double *dst, double value, int64_t count)
-{
-	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx < count)
-		dst[idx] = value;
-}
-
-// acc[0] += #ok, acc[1+i] += sum (y_i - shift_i), acc[1+n+i] += sum (y_i - shift_i)^2 over trajectories with status OK
-__global__ void k_moments(const double *y, const int *status, int64_t B, int n, const double *shift, double *acc)
-{
-	extern __shared__ double sh[];  // [blockDim.x / 32][1 + 2n]
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-	const int width = 1 + 2 * n;
-	for (int f = 0; f < width; f++) {
-		double part = 0.0;
-		for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < B; k += (int64_t)gridDim.x * blockDim.x) {
-			if (status[k] != TRAJ_OK)
-				continue;
-			if (f == 0)
-				part += 1.0;
-			else {
-				const int i = (f - 1) % n;
-				const double d = y[(int64_t)i * B + k] - shift[i];
-				part += (f <= n) ? d : d * d;
-			}
-		}
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1)
-			part += __shfl_xor_sync(0xffffffffu, part, o);
-		if (lane == 0)
-			sh[warp * width + f] = part;
-	}
-	__syncthreads();
-	for (int f = threadIdx.x; f < width; f += blockDim.x) {
-		double s = 0.0;
-		for (int w = 0; w < nw; w++)
-			s += sh[w * width + f];
-		atomicAdd(&acc[f], s);
-	}
-}
-
-// FP64 peak: 8 independent dependent-chains of DFMA per thread
-__global__ void k_dfma_peak(double *sink, int iters)
-{
-	double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-	const double m = 0.999999, b = 1e-7;
-	for (int i = 0; i < iters; i++) {
-		a0 = __fma_rn(a0, m, b); a1 = __fma_rn(a1, m, b); a2 = __fma_rn(a2, m, b); a3 = __fma_rn(a3, m, b);
-		a4 = __fma_rn(a4, m, b); a5 = __fma_rn(a5, m, b); a6 = __fma_rn(a6, m, b); a7 = __fma_rn(a7, m, b);
-	}
-	const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-	if (s == 123.456)
-		sink[0] = s;
-}
-
-__global__ void k_debug_log(const double *x, double *out, int64_t count)
-{
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < count)
-		out[i] = jsde_log(x[i]);
-}
-
-// out[i] = a[i]/b[i] through the shared-divisor path (exact_div.cuh); tame[i] tells whether that path vouches for it
-__global__ void k_debug_shared_div(const double *a, const double *b, double *out, unsigned char *tame, int64_t count)
-{
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < count) {
-		bool ok = true;
-		const SharedDivisor d(b[i]);
-		out[i] = d.divide(a[i], ok);
-		tame[i] = ok ? 1 : 0;
-	}
-}
-
-__global__ void k_debug_pow(const double *x, double yexp, double *out, int64_t count)
-{
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < count)
-		out[i] = jsde_pow(x[i], yexp);
 }
 
 }  // namespace jsde

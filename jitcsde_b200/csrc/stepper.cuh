@@ -18,8 +18,6 @@
 
 namespace jsde {
 
-enum { TRAJ_OK = 0, TRAJ_MIN_STEP = 1, TRAJ_NOISE_OVERFLOW = 2 };
-
 template <class Model>
 struct Lane {
 	static constexpr int N = Model::N;

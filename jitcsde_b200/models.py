@@ -50,7 +50,56 @@ ou_timedep = ModelSpec("ou_timedep", 2, True, ("-1.0*y(0)+t", "-0.5*(y(1)-1.0)")
 #: scalar validation SDE of `tests/validation.py:21-32` without the exponential (polynomial part only)
 cubic = ModelSpec("cubic", 1, True, ("-(y(0)*y(0)*y(0))+4*y(0)+y(0)*y(0)",), ("3.0",))
 
+
+
+def fhn_network(units: int, name: str, seed: int = 7) -> ModelSpec:
+	"""
+	Noisy FitzHugh–Nagumo network with dense coupling (SURVEY §8 d config 5; units=500 gives n=1000):
+	    dv_i = v_i - v_i^3/3 - w_i + I + (K/N) sum_j A_ij (v_j - v_i),    dw_i = eps (v_i + a - b w_i),
+	additive noise sigma on v only.  y(i) = v_i for i < units, y(units+i) = w_i.  A = default_rng(seed).random, stored
+	transposed so that threads owning neighbouring components read neighbouring table entries; the sum runs over j in
+	ascending order on both the device and the oracle (same rounding).
+	"""
+	import numpy as np
+	A = np.random.default_rng(seed).random((units, units))
+	table = ",".join(float(v).hex() for v in A.T.ravel())
+	preamble = f"""
+#ifndef JSDE_MODEL_FN
+#define JSDE_MODEL_FN static inline
+#define JSDE_MODEL_CONST static const
+#endif
+#define FHN_UNITS {units}
+JSDE_MODEL_CONST double FHN_AT[FHN_UNITS * FHN_UNITS] = {{{table}}};
+JSDE_MODEL_FN double fhn_drift(int i, const double *Y)
+{{
+	if (i < FHN_UNITS) {{
+		double s = 0.0;
+		for (int j = 0; j < FHN_UNITS; j++)
+			s += FHN_AT[j * FHN_UNITS + i] * (Y[j] - Y[i]);
+		return Y[i] - Y[i] * Y[i] * Y[i] / 3.0 - Y[FHN_UNITS + i] + 0.5 + (1.0 / FHN_UNITS) * s;
+	}}
+	const int u = i - FHN_UNITS;
+	return 0.08 * (Y[u] + 0.7 - 0.8 * Y[i]);
+}}
+"""
+	return ModelSpec(name, 2 * units, True, (), (), preamble=preamble,
+		f_component="fhn_drift(i, Y)", g_component="(i < FHN_UNITS ? 0.05 : 0.0)")
+
+
+#: small network for the parity tests of the wide (block-per-trajectory) kernel
+fhn_small = fhn_network(24, "fhn_small")
+_FHN_1000 = None
+
+
+def fhn_1000() -> ModelSpec:
+	"""n = 1000 (BASELINE.json configs[4]); built lazily: its coupling table is a 6 MB literal"""
+	global _FHN_1000
+	if _FHN_1000 is None:
+		_FHN_1000 = fhn_network(500, "fhn_1000")
+	return _FHN_1000
+
+
 ALL = {m.name: m for m in (
 	lorenz_additive, lorenz_additive_fixture, lorenz_multiplicative, lorenz_jumpy,
-	gbm, gbm_pars, duffing, ou, ou_timedep, cubic,
+	gbm, gbm_pars, duffing, ou, ou_timedep, cubic, fhn_small,
 )}

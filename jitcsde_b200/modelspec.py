@@ -46,8 +46,24 @@ class ModelSpec:
 	preamble: str = ""
 	f_body: str = ""
 	g_body: str = ""
+	# "Wide" models (large n, e.g. the 1000-dimensional network of SURVEY §8 d config 5): instead of n printed
+	# expressions, ONE expression in the component index `i` (and y(j), t, parameters, helpers from `preamble`).
+	# The GPU runs one thread block per trajectory with the components spread over the threads; the oracle loops
+	# over i.  `preamble` may use JSDE_MODEL_FN (function qualifier) and JSDE_MODEL_CONST (table qualifier).
+	f_component: str = ""
+	g_component: str = ""
+
+	@property
+	def wide(self) -> bool:
+		return bool(self.f_component)
 
 	def __post_init__(self):
+		if self.wide:
+			assert self.g_component, "wide models need g_component too"
+			assert self.additive, "wide models are implemented for additive noise (SRA) only"
+			assert self.jump is None
+			object.__setattr__(self, "f_body", f"for (int i = 0; i < {self.n}; i++) set_drift(i, {self.f_component});\n")
+			object.__setattr__(self, "g_body", f"for (int i = 0; i < {self.n}; i++) set_diffusion(i, {self.g_component});\n")
 		if not self.f_body:
 			assert len(self.f) == self.n, "len(f) != n"
 		if not self.g_body:
@@ -56,7 +72,7 @@ class ModelSpec:
 	def digest(self) -> str:
 		h = hashlib.sha256()
 		for part in (self.name, str(self.n), str(self.additive), *self.f, "|", *self.g, "|", *self.control_pars,
-				"|", *(self.jump.amp if self.jump else ()), "|", self.preamble, self.f_body, self.g_body):
+				"|", *(self.jump.amp if self.jump else ()), "|", self.preamble, self.f_body, self.g_body, self.f_component, self.g_component):
 			h.update(part.encode())
 			h.update(b"\0")
 		return h.hexdigest()[:16]

