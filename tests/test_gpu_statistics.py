@@ -104,3 +104,36 @@ def test_multiplicative_full_size_sample():
 	ref = port.run_ensemble(spec, y0[idx], sharding.global_seeds(0, B)[idx], 0.0, T)
 	assert_bits_equal(y[idx], ref["y"], "sampled trajectories")
 	assert (E.status == 0).all()
+
+
+def test_config3_duffing_full_size_sample():
+	"""BASELINE.json configs[2]: stochastic Duffing ensemble, multiplicative noise (SRI), 2^20 trajectories"""
+	spec, B, T = models.duffing, 1 << 20, 1.0
+	E, stats, y0 = run(spec, B, T)
+	y = E.get_state()
+	idx = np.arange(0, B, B // 64)
+	ref = port.run_ensemble(spec, y0[idx], sharding.global_seeds(0, B)[idx], 0.0, T)
+	assert_bits_equal(y[idx], ref["y"], "sampled trajectories")
+	assert (E.status == 0).all() and (E.t == T).all()
+
+
+def test_config4_jumpy_lorenz_full_size_sample():
+	"""BASELINE.json configs[3]: examples/noisy_and_jumpy_lorenz.py physics, 2^18 trajectories, per-trajectory jump tape"""
+	from util import jump_tape
+	spec, B, T, L = models.lorenz_jumpy, 1 << 18, 2.0, 24
+	rng = np.random.default_rng(5)
+	taus = rng.exponential(1.0, (B, L))
+	xis = rng.standard_normal((B, L))
+	y0 = sharding.global_initial_states(0, B, 3)
+	E = Ensemble(spec, B)
+	E.seed(sharding.global_seeds(0, B))
+	E.set_state(y0, 0.0)
+	E.set_integration_parameters(ControllerParameters())
+	stats = E.integrate_jumps(T, taus, xis)
+	y = E.get_state()
+	assert (E.status == 0).all() and (E.t == T).all() and np.isfinite(y).all()
+	expected_jumps = int(((np.cumsum(taus, axis=1) < T).sum(axis=1)).sum())
+	assert stats["jumps"] == expected_jumps
+	for k in range(0, B, B // 32):
+		P = port.PortCore(spec, y0[k], 0.0, int(k))
+		assert_bits_equal(y[k], P.integrate_jumps(T, taus[k], xis[k]), f"trajectory {k}")
