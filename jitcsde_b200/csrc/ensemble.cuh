@@ -6,9 +6,12 @@
 //   y        [n][B]      state                                   (reference: sde_integrator.state, template:29)
 //   t, dt    [B]         time, controller step size              (template:30; _jitcsde.py self.dt)
 //   new_y, err [n][B], new_t [B]   last proposal                 (template:31-33) — only the single-step surface uses them
-//   q        [D][B][IT]  noise memory (template:15-21) as a bounded array instead of a list: item d of trajectory b is
-//                        {h, DW[n], DZ[n]} padded to IT = 2*ceil((1+2n)/2) doubles; item 0 starts at the current time
-//   q_count, q_cursor [B]
+//   q        [DP][B][IT] noise memory (template:15-21) as a bounded ring instead of a list: DP = D rounded up to a power
+//                        of two; item d of trajectory b lives in slot (q_head[b] + d) mod DP and is {h, DW[n], DZ[n]}
+//                        padded to IT = 2*ceil((1+2n)/2) doubles; item 0 starts at the current time.  Dropping the
+//                        consumed items (accept_step) advances the head; a Brownian-bridge insertion moves whichever
+//                        side of the insertion point is shorter (usually nothing)
+//   q_count, q_cursor, q_head [B]
 //   mt       [B][156] uint4   generator state, one contiguous 2496-byte record per trajectory (random_numbers.c:31-38);
 //                             positions of different trajectories drift apart (rejections), so records are lane-private
 //   mt_chunk [B]         next 4-word chunk to generate (the reference's `pos` / 4, running ahead by the queued pairs)
@@ -40,11 +43,12 @@ struct CallTotals {
 
 struct EnsembleView {
 	int64_t B;
-	int D;  // noise capacity (items)
+	int D;      // noise capacity (items)
+	int Dmask;  // physical ring size - 1 (power of two >= D)
 	double *y, *t, *dt;
 	double *new_y, *err, *new_t;
-	double *q;  // [D][B][IT]
-	int *q_count, *q_cursor;
+	double *q;  // [Dmask + 1][B][IT]
+	int *q_count, *q_cursor, *q_head;
 	uint4 *mt;
 	int *mt_chunk;
 	double *rng_spill;  // [CAP][3][B] accepted-but-unconsumed pairs (x1, x2, r2) between kernel launches

@@ -120,7 +120,15 @@ JSDE_FN int jsde_pow_in_domain(double x, double y)
 	return ix > 0 && ix < 0x7ff0000000000000ULL && ay >= 0x3be0000000000000ULL /*2^-65*/ && ay <= 0x3ff0000000000000ULL /*1*/;
 }
 
-JSDE_FN double jsde_pow(double x, double y)
+// where the lookups go: the tables of glibc_tables.h (host; device: constant memory — fine for a warp-uniform caller)
+// or copies of them staged in shared memory by the caller (the lane-per-trajectory controller looks up 32 different
+// entries at once, which constant memory would serialise)
+typedef struct {
+	const double *invc, *logc, *logctail;
+	const unsigned long long *exp_tab;
+} jsde_pow_tables;
+
+JSDE_FN double jsde_pow_with(double x, double y, const jsde_pow_tables T)
 {
 	uint64_t ix = JSDE_ASU(x);
 	if ((ix >> 52) == 0) {
@@ -136,9 +144,9 @@ JSDE_FN double jsde_pow(double x, double y)
 	const uint64_t iz = ix - (tmp & (0xfffULL << 52));
 	const double z = JSDE_ASD(iz);
 	const double kd = (double)k;
-	const double invc = JSDE_PTAB(JSDE_POW_INVC, i);
-	const double logc = JSDE_PTAB(JSDE_POW_LOGC, i);
-	const double logctail = JSDE_PTAB(JSDE_POW_LOGCTAIL, i);
+	const double invc = T.invc[i];
+	const double logc = T.logc[i];
+	const double logctail = T.logctail[i];
 	const double t1 = JSDE_FMA(kd, JSDE_LN2HI, logc);
 	const double lo1 = JSDE_FMA(kd, JSDE_LN2LO, logctail);
 	const double r = JSDE_FMA(z, invc, -1.0);
@@ -170,11 +178,17 @@ JSDE_FN double jsde_pow(double x, double y)
 	double rr = JSDE_FMA(kd2, JSDE_EXP_NEGLN2LON, JSDE_FMA(kd2, JSDE_EXP_NEGLN2HIN, ehi));
 	rr = elo + rr;
 	const int idx = 2 * (int)(ki & 127);
-	const double tail = JSDE_ASD(JSDE_PTAB(JSDE_EXP_TAB, idx));
-	const uint64_t sbits = JSDE_PTAB(JSDE_EXP_TAB, idx + 1) + (ki << 45);
+	const double tail = JSDE_ASD(T.exp_tab[idx]);
+	const uint64_t sbits = T.exp_tab[idx + 1] + (ki << 45);
 	const double scale = JSDE_ASD(sbits);
 	const double rr2 = rr * rr;
 	const double q = JSDE_FMA(JSDE_FMA(rr, JSDE_EXP_C3, JSDE_EXP_C2), rr2, rr + tail);
 	const double tm = JSDE_FMA(JSDE_FMA(rr, JSDE_EXP_C5, JSDE_EXP_C4), rr2 * rr2, q);
 	return JSDE_FMA(tm, scale, scale);
+}
+
+JSDE_FN double jsde_pow(double x, double y)
+{
+	const jsde_pow_tables T = {JSDE_POW_INVC, JSDE_POW_LOGC, JSDE_POW_LOGCTAIL, JSDE_EXP_TAB};
+	return jsde_pow_with(x, y, T);
 }

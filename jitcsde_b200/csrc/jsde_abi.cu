@@ -97,6 +97,7 @@ int reset_integrator(jsde_handle *h)
 	const int64_t B = h->B;
 	CU(cudaMemsetAsync(h->v.q_count, 0, B * sizeof(int), h->stream));
 	CU(cudaMemsetAsync(h->v.q_cursor, 0, B * sizeof(int), h->stream));
+	CU(cudaMemsetAsync(h->v.q_head, 0, B * sizeof(int), h->stream));
 	CU(cudaMemsetAsync(h->v.status, 0, B * sizeof(int), h->stream));
 	CU(cudaMemsetAsync(h->v.accepted, 0, B * sizeof(unsigned long long), h->stream));
 	CU(cudaMemsetAsync(h->v.rejected, 0, B * sizeof(unsigned long long), h->stream));
@@ -174,11 +175,14 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	EnsembleView &v = h->v;
 	v.B = B;
 	v.D = h->D;
+	int ring = 2;
+	while (ring < h->D) ring <<= 1;
+	v.Dmask = ring - 1;
 #define ALLOC(ptr, cnt) if ((rc = dev_alloc(h, &(ptr), (size_t)(cnt)))) return bail(rc)
 	ALLOC(v.y, B * n); ALLOC(v.t, B); ALLOC(v.dt, B);
 	ALLOC(v.new_y, B * n); ALLOC(v.err, B * n); ALLOC(v.new_t, B);
-	ALLOC(v.q, (int64_t)h->D * B * noise_item_doubles(n));
-	ALLOC(v.q_count, B); ALLOC(v.q_cursor, B);
+	ALLOC(v.q, (int64_t)ring * B * noise_item_doubles(n));
+	ALLOC(v.q_count, B); ALLOC(v.q_cursor, B); ALLOC(v.q_head, B);
 	ALLOC(v.mt, B * MT_CHUNKS); ALLOC(v.mt_chunk, B);
 	ALLOC(v.rng_spill, (int64_t)WarpRng<Model::N>::CAP * 3 * B); ALLOC(v.rng_level, B);
 	ALLOC(v.status, B); ALLOC(v.accepted, B); ALLOC(v.rejected, B);
@@ -206,8 +210,9 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 		return bail(fail(JSDE_E_CUDA, cudaGetErrorString(err)));
 	// the generator FIFOs + staging area exceed the 48 KB default for dynamic shared memory
 	const int smem = (int)rng_smem_bytes<Model>();
-	if ((err = cudaFuncSetAttribute(k_integrate<Model, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
-		(err = cudaFuncSetAttribute(k_integrate<Model, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+	const int duo_smem = (int)duo_smem_bytes<Model>();
+	if ((err = cudaFuncSetAttribute(k_integrate<Model, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, duo_smem)) != cudaSuccess ||
+		(err = cudaFuncSetAttribute(k_integrate<Model, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, duo_smem)) != cudaSuccess ||
 		(err = cudaFuncSetAttribute(k_get_next_step<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
 		(err = cudaFuncSetAttribute(k_pin_noise<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
 		(err = cudaFuncSetAttribute(k_draw_gauss<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
@@ -334,10 +339,10 @@ static int integrate_common(jsde_t *h, double target_time, int use_tape, jsde_st
 	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
 	CU(cudaEventRecord(h->ev0, h->stream));
 	if (grid_times_dev)
-		k_integrate<Model, true><<<grid_for(h->B, BLOCK), BLOCK, rng_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
+		k_integrate<Model, true><<<grid_for(h->B, 32 * DUO_PAIRS), DUO_BLOCK, duo_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
 			grid_times_dev, grid_count, grid_out_dev);
 	else
-		k_integrate<Model, false><<<grid_for(h->B, BLOCK), BLOCK, rng_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
+		k_integrate<Model, false><<<grid_for(h->B, 32 * DUO_PAIRS), DUO_BLOCK, duo_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
 			nullptr, 0, nullptr);
 	CU(cudaGetLastError());
 	return finish_call(h, stats_host, 1);
@@ -586,9 +591,13 @@ int jsde_dump_noise(jsde_t *h, int64_t b, double *out_host, int max_items, int *
 	constexpr int n = Model::N;
 	CU(cudaStreamSynchronize(h->stream));
 	CU(cudaMemcpy(count, h->v.q_count + b, sizeof(int), cudaMemcpyDeviceToHost));
+	int head = 0;
+	CU(cudaMemcpy(&head, h->v.q_head + b, sizeof(int), cudaMemcpyDeviceToHost));
 	const int width = 1 + 2 * n;
-	for (int d = 0; d < *count && d < max_items; d++)
-		CU(cudaMemcpy(out_host + (size_t)d * width, h->v.q + ((int64_t)d * h->B + b) * noise_item_doubles(n), width * sizeof(double), cudaMemcpyDeviceToHost));
+	for (int d = 0; d < *count && d < max_items; d++) {
+		const int64_t slot = (head + d) & h->v.Dmask;
+		CU(cudaMemcpy(out_host + (size_t)d * width, h->v.q + (slot * h->B + b) * noise_item_doubles(n), width * sizeof(double), cudaMemcpyDeviceToHost));
+	}
 	return JSDE_OK;
 }
 

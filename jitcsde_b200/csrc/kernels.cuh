@@ -3,6 +3,7 @@
 #pragma once
 
 #include "stepper.cuh"
+#include "duo.cuh"
 #include "kernels_common.cuh"
 
 namespace jsde {
@@ -72,13 +73,37 @@ __device__ __forceinline__ WarpRng<Model::N> make_rng(const EnsembleView &e, int
 }
 
 // jitcsde.integrate (_jitcsde.py:597-630) and, with a tape, jitcsde_jump.integrate (:693-700) for every trajectory.
-// The warp alternates between (a) cooperative generator refills until every lane that still has work holds the N
-// pairs an attempt may need and (b) one attempted step per such lane.  Choosing the next target and applying a jump
-// are folded into the same loop so that lanes which jump do not serialise the warp.
+// Warp-specialised (duo.cuh): consumer warp w steps trajectories [128*block + 32*w, +32), one per lane, one attempted
+// step per round; producer warp w keeps their polar-pair FIFOs filled.  Choosing the next target and applying a jump
+// are folded into the consumer's loop so that lanes which jump do not serialise the warp.
+template <class Model>
+constexpr size_t duo_smem_bytes() { return ((size_t)DUO_PAIRS * PairLayout<Model::N>::DOUBLES + MATH_TAB_DOUBLES) * sizeof(double); }
+
 template <class Model, bool GRID>
-__global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleView e, Controller c, double target, int use_tape,
+__global__ void __launch_bounds__(DUO_BLOCK, JSDE_DUO_MIN_BLOCKS) k_integrate(EnsembleView e, Controller c, double target, int use_tape,
 	const double *__restrict__ grid_times_, int grid_count, double *__restrict__ grid_out)
 {
+	constexpr int N = Model::N;
+	extern __shared__ __align__(16) double jsde_smem[];
+	stage_math_tables(jsde_smem);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int pair = warp & (DUO_PAIRS - 1);
+	const int64_t k = ((int64_t)blockIdx.x * DUO_PAIRS + pair) * 32 + lane;
+	const bool live = k < e.B;
+	const int64_t kk = live ? k : 0;
+	double *pair_smem = jsde_smem + MATH_TAB_DOUBLES + pair * PairLayout<N>::DOUBLES;
+
+	if (warp >= DUO_PAIRS) {  // ---- producer warpgroup ----
+		setmaxnreg_dec<JSDE_DUO_PRODUCER_REGS>();
+		PairProducer<N> P(pair_smem, pair, e.mt, k - lane, live);
+		P.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+		P.run();
+		P.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+		return;
+	}
+
+	// ---- consumer warpgroup ----
+	setmaxnreg_inc<JSDE_DUO_CONSUMER_REGS>();
 	const double *grid_times = GRID ? grid_times_ : nullptr;  // compile-time nullptr keeps the plain kernel free of grid code
 	// Sampling-grid mode (grid_times != nullptr): the lane integrates to grid_times[0], records its state in
 	// grid_out[0][·][k], goes on to grid_times[1], … — exactly the sequence of integrate() calls of
@@ -86,13 +111,8 @@ __global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleVi
 	int grid_index = 0;
 	if (grid_times)
 		target = grid_times[0];
-	constexpr int N = Model::N;
-	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-	const bool live = k < e.B;
-	const int64_t kk = live ? k : 0;
-	WarpRng<N> rng = make_rng<Model>(e, k, live);
-	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
-	Lane<Model> L(e, kk, rng);
+	PairConsumer<N> rng(pair_smem, jsde_smem, pair);
+	Lane<Model, PairConsumer<N>> L(e, kk, rng);
 	unsigned acc = 0, rej = 0, jumps = 0;  // per call and trajectory: far below 2^32 (the noise memory would overflow first)
 	double next_jump = 0.0;
 	bool jump_set = false;
@@ -112,12 +132,14 @@ __global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleVi
 	}
 	bool need_target = true, to_jump = false;
 	double tgt = target;
-	while (__any_sync(0xffffffffu, active)) {
-		const bool refilled = rng.ensure(active, N);
+	bool primed = false;  // round 0 is empty: the producer fills the FIFOs for the first time
+	while (rng.rendezvous(active)) {
+		if (!primed) {
+			primed = true;
+			continue;
+		}
 		bool attempt = false, last = false;
 		double actual_dt = 0.0;
-		double I1[N], DZ[N];
-		typename Lane<Model>::NoiseScan scan;
 		if (active) {
 			attempt = true;
 			if (need_target) {
@@ -162,23 +184,17 @@ __global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleVi
 					}
 				}
 			}
-			if (attempt) {
-				if (L.t + L.dt < tgt)
-					actual_dt = L.dt;
-				else {
-					actual_dt = tgt - L.t;
-					last = true;
-				}
-				L.scan_noise(actual_dt, scan, I1, DZ);  // this round's noise-memory loads
-			}
 		}
-		if (refilled)  // warp-uniform: start fetching the next refill's generator words now that our loads are out
-			rng.stage_ahead(active, N);
 		if (attempt) {
-			if (!L.finish_noise(scan, I1, DZ))
+			if (L.t + L.dt < tgt)
+				actual_dt = L.dt;
+			else {
+				actual_dt = tgt - L.t;
+				last = true;
+			}
+			if (!L.propose(actual_dt))
 				active = false;  // noise memory overflow
 			else {
-				L.stages(actual_dt, I1, DZ);
 				const int verdict = L.adjust_step(c, actual_dt);
 				if (verdict == 1) {
 					L.commit();
@@ -218,7 +234,6 @@ __global__ void __launch_bounds__(BLOCK, JSDE_MIN_BLOCKS) k_integrate(EnsembleVi
 			}
 		}
 	}
-	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 	int failed_min = 0, failed_ovf = 0;
 	if (live) {
 		L.store();

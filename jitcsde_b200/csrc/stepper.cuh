@@ -18,7 +18,7 @@
 
 namespace jsde {
 
-template <class Model>
+template <class Model, class Rng = WarpRng<Model::N>>
 struct Lane {
 	static constexpr int N = Model::N;
 	static constexpr bool ADDITIVE = Model::ADDITIVE;
@@ -28,23 +28,23 @@ struct Lane {
 	const int64_t k;
 	static constexpr int IT = noise_item_doubles(N);  // one noise item: {h, DW[N], DZ[N]} padded to 16-byte pairs
 
-	WarpRng<N> &rng;
+	Rng &rng;  // source of accepted polar pairs: pop(x1, x2, r2) and the shared-memory log table
 	double *const q0;  // item 0 of this trajectory's noise memory; item d is at q0 + d*B*IT
 
 	double y[N], t, dt;
 	double ny[N], er[N], nt;  // last proposal
 	double par[NP > 0 ? NP : 1];
-	int count, cursor, status;
+	int count, cursor, head, status;  // noise memory: depth, items used by the last proposal, ring slot of item 0
 	unsigned fresh;
 	int max_depth;
 
-	__device__ __forceinline__ Lane(const EnsembleView &view, int64_t index, WarpRng<N> &source)
+	__device__ __forceinline__ Lane(const EnsembleView &view, int64_t index, Rng &source)
 		: e(view), k(index), rng(source), q0(view.q + index * IT), fresh(0), max_depth(0) {}
 
 	// ---- global-memory accessors ---------------------------------------------------------------------------
-	// Noise memory: items of IT doubles, [D][B][IT]; a warp's 32 items of one depth are 32*IT*8 contiguous bytes and an
-	// item moves as IT/2 16-byte vectors.
-	__device__ __forceinline__ double *item_ptr(int d) const { return q0 + (int64_t)d * e.B * IT; }
+	// Noise memory: items of IT doubles in a ring of slots, [slot][B][IT]; a warp's 32 items of one slot are 32*IT*8
+	// contiguous bytes and an item moves as IT/2 16-byte vectors.  Logical item d sits in slot (head + d) mod ring size.
+	__device__ __forceinline__ double *item_ptr(int d) const { return q0 + (int64_t)((head + d) & e.Dmask) * e.B * IT; }
 
 	__device__ __forceinline__ void load_item(int d, double &h, double (&W)[N], double (&Z)[N]) const
 	{
@@ -99,6 +99,7 @@ struct Lane {
 		dt = e.dt[k];
 		count = e.q_count[k];
 		cursor = e.q_cursor[k];
+		head = e.q_head[k];
 		status = e.status[k];
 #pragma unroll
 		for (int i = 0; i < NP; i++)
@@ -114,6 +115,7 @@ struct Lane {
 		e.dt[k] = dt;
 		e.q_count[k] = count;
 		e.q_cursor[k] = cursor;
+		e.q_head[k] = head;
 		e.status[k] = status;
 	}
 
@@ -237,9 +239,19 @@ struct Lane {
 			draw(scale, gW, gZ);
 			fresh++;
 			if (bridging) {
+				// make room for one more item at the cursor (the reference relinks its list): shift whichever side is
+				// shorter — the items behind the cursor up, or the already consumed ones in front of it down (the ring
+				// has a free slot before its head).  The usual case, a bridge over the first or the last item, moves nothing.
+				if (s.cur <= count - 1 - s.cur) {
+					head = (head - 1) & e.Dmask;
 #pragma unroll 1
-				for (int d = count - 1; d > s.cur; d--)  // make room behind the cursor (the reference relinks its list)
-					move_item(d + 1, d);
+					for (int d = 0; d < s.cur; d++)
+						move_item(d, d + 1);
+				} else {
+#pragma unroll 1
+					for (int d = count - 1; d > s.cur; d--)
+						move_item(d + 1, d);
+				}
 				double w2[N], z2[N];
 #pragma unroll
 				for (int i = 0; i < N; i++) {
@@ -415,13 +427,8 @@ struct Lane {
 		for (int i = 0; i < N; i++)
 			y[i] = ny[i];
 		t = nt;
-		const int rest = count - cursor;
-		if (cursor > 0) {
-#pragma unroll 1
-			for (int d = 0; d < rest; d++)
-				move_item(d, d + cursor);
-		}
-		count = rest;
+		head = (head + cursor) & e.Dmask;
+		count -= cursor;
 		cursor = 0;
 	}
 
@@ -435,7 +442,7 @@ struct Lane {
 		// one call site for both uses of Python's `**` (:587, :592) so that rejecting and growing lanes share it
 		double pw = 0.0;  // inf ** negative = 0.0
 		if ((rejecting && p <= 1.7976931348623157e308) || (growing && p != 0.0))
-			pw = jsde_pow(p, rejecting ? c.shrink_exp : c.grow_exp);
+			pw = jsde_pow_with(p, rejecting ? c.shrink_exp : c.grow_exp, rng.pow_tables());
 		if (rejecting) {
 			const double shrink = c.safety * pw;
 			dt = actual_dt * (c.min_factor > shrink ? c.min_factor : shrink);

@@ -39,8 +39,9 @@ constexpr int RNG_STAGE_CHUNKS = 18;   // per entry: chunks c..c+8 and c+99..c+1
 
 template <int N>
 struct WarpRng {
-	// room for the pairs left over below one draw's need (N-1) plus a full group
-	static constexpr int CAP = N - 1 + RNG_GROUP;
+	// room for the pairs left over below two draws' need (2N-1) plus a full group: the producer warps of the fused
+	// integrate kernel (duo.cuh) keep every trajectory one draw ahead of its consumer; the spill format is shared
+	static constexpr int CAP = 2 * N - 1 + RNG_GROUP;
 	static constexpr int FIFO_DOUBLES = (3 * CAP * RNG_STRIDE + 1) & ~1;  // even: keeps the staging area 16-byte aligned
 	// FIFOs | order_()[32] bytes | stage_of_()[32] bytes | staged state words
 	static constexpr int SMEM_DOUBLES_PER_WARP = FIFO_DOUBLES + 4 + 4 + RNG_STAGE_ENTRIES * RNG_STAGE_CHUNKS * 2;
@@ -61,6 +62,9 @@ struct WarpRng {
 
 	__device__ __forceinline__ WarpRng(double *smem_warp, const double *shared_log_tab, uint4 *mt, int64_t k_lane0, bool live)
 		: fx1(smem_warp), log_tab(shared_log_tab), S0(mt + k_lane0 * MT_CHUNKS), lane(threadIdx.x & 31), rd(0), lvl(0), chunk(0), usable(live) {}
+
+	// the single-step kernels never run the controller; constant-memory tables keep Lane<> instantiable with this source
+	__device__ __forceinline__ jsde_pow_tables pow_tables() const { return jsde_pow_tables{JSDE_POW_INVC, JSDE_POW_LOGC, JSDE_POW_LOGCTAIL, JSDE_EXP_TAB}; }
 
 	// ---- persistence across kernel launches: spill [CAP][3][B] + level; read slot is normalised to 0 ---------------
 	__device__ __forceinline__ void load(const double *spill, const int *levels, const int *chunks, int64_t B, int64_t k)
