@@ -183,9 +183,9 @@ struct PairProducer {
 	// Stage entry of one trajectory: chunks c..c+8 at [0..8], chunks c+99..c+107 at [9..17].
 	__device__ __forceinline__ void stage_slot(int s, int nserved, int g, int j) const
 	{
-		const int rank = 4 * s + g;
-		const bool have = rank < nserved;
-		const int T = have ? L::order(base)[rank] : 0;
+		const int rank = (4 * s + g) & 31;
+		const bool have = 4 * s + g < nserved;
+		const int T = L::order(base)[rank] & 31;  // absent ranks: a stale but valid lane number, only ever used for shuffles
 		const int c = __shfl_sync(0xffffffffu, chunk, T);
 		if (have) {
 			const uint4 *ST = S0 + T * MT_CHUNKS;
@@ -223,7 +223,7 @@ struct PairProducer {
 			__syncwarp();
 			const int rank = 4 * s + g;
 			const bool have = rank < nserved;
-			const int T = have ? L::order(base)[rank] : 0;
+			const int T = L::order(base)[rank] & 31;
 			const int c = mt_wrap(__shfl_sync(full, chunk, T) + j);
 			const int wrT = __shfl_sync(full, wr, T);
 			bool ok = false;
@@ -233,10 +233,10 @@ struct PairProducer {
 				const uint4 a = E[j], tap = E[9 + j];
 				const uint32_t next = E[j + 1].x, tap_hi = E[10 + j].x;
 				uint4 r;
-				r.x = tap.y ^ mt_mix(a.x, a.y);
-				r.y = tap.z ^ mt_mix(a.y, a.z);
-				r.z = tap.w ^ mt_mix(a.z, a.w);
-				r.w = tap_hi ^ mt_mix(a.w, next);
+				r.x = mt_twist(a.x, a.y, tap.y);
+				r.y = mt_twist(a.y, a.z, tap.z);
+				r.z = mt_twist(a.z, a.w, tap.w);
+				r.w = mt_twist(a.w, next, tap_hi);
 				S0[T * MT_CHUNKS + c] = r;
 				uint4 v;
 				v.x = mt_temper(a.x);

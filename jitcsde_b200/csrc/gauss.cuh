@@ -19,11 +19,25 @@ __device__ __forceinline__ double polar_coordinate(uint32_t w_hi, uint32_t w_lo)
 	return __ll2double_rn((long long)k - (1LL << 52)) * 0x1p-52;
 }
 
+// The same value without the 64-bit integer-to-double conversion: with a = w_hi>>5 (27 bit), b = w_lo>>6 (26 bit),
+// 2u-1 = a*2^-26 + b*2^-52 - 1.  The doubles 2^52+a and 2^52+b are formed by placing a, b in the low mantissa word
+// under the exponent of 2^52; (2^52+a)*2^-26 - 2^26 = a*2^-26 and (2^52+b)*2^-52 - 2 = b*2^-52 - 1 are exact as fused
+// operations (multiples of 2^-26 below 2, resp. of 2^-52 in (-1, 0)), and so is their sum (a multiple of 2^-52 of
+// magnitude below 1).  Three FP64 operations, no conversion unit.
+__device__ __forceinline__ double polar_coordinate_exact(uint32_t w_hi, uint32_t w_lo)
+{
+	const double A = __hiloint2double(0x43300000, (int)(w_hi >> 5));
+	const double B = __hiloint2double(0x43300000, (int)(w_lo >> 6));
+	const double ta = __fma_rn(A, 0x1p-26, -0x1p26);
+	const double tb = __fma_rn(B, 0x1p-52, -2.0);
+	return __dadd_rn(ta, tb);
+}
+
 // `w` = four tempered words in stream order.  Returns true iff the reference's do-while would leave the loop.
 __device__ __forceinline__ bool polar_candidate(uint4 w, double &x1, double &x2, double &r2)
 {
-	x2 = polar_coordinate(w.x, w.y);
-	x1 = polar_coordinate(w.z, w.w);
+	x2 = polar_coordinate_exact(w.x, w.y);
+	x1 = polar_coordinate_exact(w.z, w.w);
 	r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
 	return r2 < 1.0 && r2 != 0.0;
 }

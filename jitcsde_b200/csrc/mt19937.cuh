@@ -31,6 +31,17 @@ __device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b)
 	return (y >> 1) ^ ((b & 1u) ? 0x9908b0dfu : 0u);
 }
 
+// tap ^ mt_mix(a, b) in five instructions (bit select, shift, bit test, multiply on the otherwise idle FMA pipe,
+// three-input xor) instead of the seven the compiler makes of the expression above
+__device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b, uint32_t tap)
+{
+	uint32_t y;
+	asm("lop3.b32 %0, %1, %2, 0x80000000, 0xE4;" : "=r"(y) : "r"(a), "r"(b));  // (mask & a) | (~mask & b)
+	const uint32_t mag = (b & 1u) * 0x9908b0dfu;
+	return (y >> 1) ^ mag ^ tap;
+}
+
+
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
 {
 	y ^= y >> 11;
@@ -40,7 +51,8 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
 	return y;
 }
 
-__device__ __forceinline__ int mt_wrap(int c) { return c >= MT_CHUNKS ? c - MT_CHUNKS : c; }
+// c mod 156 for c in [0, 312): unsigned minimum of c and c - 156 (which wraps around to a huge value when c < 156)
+__device__ __forceinline__ int mt_wrap(int c) { return (int)min((unsigned)c, (unsigned)c - 156u); }
 
 // Consume chunk `c` of the trajectory whose state starts at `S` (156 uint4): returns the four *untempered* words and
 // writes their replacements.

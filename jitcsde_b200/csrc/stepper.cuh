@@ -228,13 +228,13 @@ struct Lane {
 				return false;
 			}
 			const bool bridging = s.cur < count;  // then the scan left the too-long item in (hq, qW, qZ)
-			double h_exc = 0.0, factor = 0.0, scale;
-			if (bridging) {  // Brownian_bridge (template:178-202)
+			double h_exc = 0.0, factor = 0.0, variance = s.need;  // append_noise (template:170-176): scale = sqrt(h_need)
+			if (bridging) {  // Brownian_bridge (template:178-202): scale = sqrt(factor*h_need)
 				h_exc = s.hq - s.need;
 				factor = h_exc / s.hq;
-				scale = sqrt(factor * s.need);
-			} else  // append_noise (template:170-176)
-				scale = sqrt(s.need);
+				variance = factor * s.need;
+			}
+			const double scale = sqrt(variance);  // one square root for both kinds of lanes
 			double gW[N], gZ[N];
 			draw(scale, gW, gZ);
 			fresh++;
