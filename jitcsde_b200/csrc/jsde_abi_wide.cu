@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -55,6 +56,7 @@ struct jsde_handle {
 	int device = 0;
 	int64_t B = 0;
 	int D = 0;
+	int tpb = 1;  // trajectories per thread block (wide.cuh)
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	WideView v{};
@@ -91,9 +93,51 @@ int reset_integrator(jsde_handle *h)
 	CU(cudaMemsetAsync(h->v.accepted, 0, B * sizeof(unsigned long long), h->stream));
 	CU(cudaMemsetAsync(h->v.rejected, 0, B * sizeof(unsigned long long), h->stream));
 	k_iota_rows<<<grid_for(B * h->D, 256), 256, 0, h->stream>>>(h->v.order, B, h->D);
-	k_wide_seed<<<grid_for(B, 64), 64, 0, h->stream>>>(h->v.key, h->v.fifo_rd, h->v.fifo_cnt, h->seeds, B);
+	k_wide_seed<<<grid_for(B, 64), 64, 0, h->stream>>>(h->v.key, h->v.pos, h->seeds, B);
 	CU(cudaGetLastError());
 	return JSDE_OK;
+}
+
+// One block integrates `tpb` trajectories (wide.cuh).  tpb is chosen so that the ensemble fills the GPU's block slots
+// (2 blocks per SM) in one wave where possible: 2^11 trajectories on 148 SMs -> 7 per block, 293 blocks on 296 slots.
+template <int T>
+int launch_one(jsde_handle *h, double target_time)
+{
+	const size_t smem = wide_smem_bytes<Model, T>();
+	CU(cudaFuncSetAttribute(k_wide_integrate<Model, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_wide_integrate<Model, T><<<grid_for(h->B, T), WBLOCK, smem, h->stream>>>(h->v, h->ctrl, target_time);
+	CU(cudaGetLastError());
+	return JSDE_OK;
+}
+
+int launch_integrate(jsde_handle *h, double target_time)
+{
+	switch (h->tpb) {
+	case 1: return launch_one<1>(h, target_time);
+	case 2: return launch_one<2>(h, target_time);
+	case 4: return launch_one<4>(h, target_time);
+	case 6: return launch_one<6>(h, target_time);
+	case 7: return launch_one<7>(h, target_time);
+	default: return launch_one<8>(h, target_time);
+	}
+}
+
+int choose_tpb(int device, int64_t B)
+{
+	static const int allowed[] = {1, 2, 4, 6, 7, 8};
+	if (const char *env = getenv("JSDE_WIDE_TPB")) {  // development / test knob
+		const int want = atoi(env);
+		for (int a : allowed)
+			if (a == want) return a;
+	}
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+		return 8;
+	const int64_t slots = 2 * (int64_t)prop.multiProcessorCount;
+	const int64_t need = (B + slots - 1) / slots;  // trajectories per block for a single wave
+	for (int a : allowed)
+		if (a >= need) return a;
+	return 8;
 }
 
 }  // namespace
@@ -142,6 +186,7 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	h->B = B;
 	h->D = noise_capacity ? noise_capacity : 32;
 	if (h->D < 2) h->D = 2;
+	h->tpb = choose_tpb(device, B);
 	constexpr int n = Model::N;
 	int rc = bind(h);
 	auto bail = [&](int code) { jsde_destroy(h); return code; };
@@ -155,7 +200,8 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 #define ALLOC(ptr, cnt) if ((rc = dev_alloc(h, &(ptr), (size_t)(cnt)))) return bail(rc)
 	ALLOC(v.y, B * n); ALLOC(v.t, B); ALLOC(v.dt, B);
 	ALLOC(v.qh, B * h->D); ALLOC(v.qw, B * h->D * 2 * n); ALLOC(v.order, B * h->D); ALLOC(v.q_count, B);
-	ALLOC(v.key, B * MT_WORDS); ALLOC(v.fifo, B * 3 * CANDIDATES); ALLOC(v.fifo_rd, B); ALLOC(v.fifo_cnt, B);
+	ALLOC(v.key, B * MT_WORDS); ALLOC(v.pos, B);
+	ALLOC(v.arg, B * n); ALLOC(v.sW, B * n); ALLOC(v.sZ, B * n); ALLOC(v.sF1, B * n); ALLOC(v.sNY, B * n);
 	ALLOC(v.status, B); ALLOC(v.accepted, B); ALLOC(v.rejected, B); ALLOC(v.totals, 1);
 	ALLOC(h->seeds, B); ALLOC(h->par, Model::NPAR > 0 ? Model::NPAR : 1); ALLOC(h->shift, n);
 #undef ALLOC
@@ -253,8 +299,7 @@ int jsde_integrate(jsde_t *h, double target_time, jsde_stats *stats_host)
 	if (rc) return rc;
 	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
 	CU(cudaEventRecord(h->ev0, h->stream));
-	k_wide_integrate<Model><<<(unsigned)h->B, WBLOCK, 0, h->stream>>>(h->v, h->ctrl, target_time);
-	CU(cudaGetLastError());
+	if ((rc = launch_integrate(h, target_time))) return rc;
 	CallTotals tot;
 	CU(cudaEventRecord(h->ev1, h->stream));
 	CU(cudaMemcpyAsync(&tot, h->v.totals, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));

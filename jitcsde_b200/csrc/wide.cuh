@@ -1,16 +1,25 @@
-// "Wide" path: one thread block per trajectory, the n components spread over the threads (SURVEY.md §8 d config 5:
-// noisy FitzHugh–Nagumo network, n = 1000, dense 500x500 coupling).  The lane-per-trajectory kernels keep a whole
-// state in one thread's registers, which stops making sense beyond a handful of components; here the state lives in
-// shared memory, every thread owns components tid, tid+256, ..., and the parts of the algorithm that are scalar per
-// trajectory (noise-memory bookkeeping, controller) are evaluated redundantly by all threads on identical inputs, so
-// that no broadcast is needed and control flow stays uniform.
+// "Wide" path for large state vectors (SURVEY.md §8 d config 5: noisy FitzHugh–Nagumo network, n = 1000, dense
+// 500x500 coupling): one 256-thread block integrates T (<= 8) trajectories in lock-step rounds, one attempted step per
+// trajectory and round.  The lane-per-trajectory kernels keep a whole state in one thread's registers, which stops
+// making sense beyond a handful of components; here per-trajectory vectors live in global memory (they are small
+// next to the coupling matrix and stay in L2) and the work is split by phase:
+//
+//   * per-trajectory, sequential-stream work — noise memory lookup, the Gaussian draw from the trajectory's ONE
+//     Mersenne Twister stream, Brownian bridge, controller — is done by one WARP per trajectory, concurrently for the
+//     T trajectories, without block-wide barriers;
+//   * the dense coupling  c_i = sum_j A_ij (y_j - y_i)  — 2*units^2 subtract/multiply/add per evaluation, > 95 % of the
+//     arithmetic — is evaluated for ALL T trajectories at once: every thread owns <= 2 rows i and keeps 2 x T partial
+//     sums in registers, so one load of A_ij (L2 -> register, coalesced over i) and one 64-byte broadcast of
+//     y_j[0..T) from shared memory feed 6 T FP64 instructions.  The sum over j runs in ascending order with separately
+//     rounded multiply and add, exactly like the oracle's loop, so results stay bit-identical (this is also why the
+//     FP64 tensor-core MMA is not used: it fuses and re-associates);
+//   * elementwise stage algebra is done by the whole block, trajectory after trajectory.
 //
 // Same algorithm and the same bits as the reference, restated for this shape:
-//   generator ........ jitcsde/random_numbers.c:41-130.  One trajectory needs n pairs per draw from ONE sequential
-//                      stream, so the block regenerates the whole 624-word state at once (the reference's batch twist,
-//                      :73-84, in three data-parallel phases), forms the block's 156 polar candidates in parallel,
-//                      compacts the accepted ones in stream order (ballot + prefix sum) and hands pair k of a draw to
-//                      the thread that owns component k.  Accepted pairs beyond a draw's need stay queued.
+//   generator ........ jitcsde/random_numbers.c:41-130: batch twist (:73-84) by one warp on a state held in shared
+//                      memory; candidates are formed 32 at a time, the accepted ones compacted in stream order by
+//                      ballot/popc; pair k of a draw belongs to component k (get_gauss, jitced_template.c:145-154).
+//                      The stream position `pos` is kept like the reference's rk_state.pos (no queue of spare pairs).
 //   noise memory ..... jitced_template.c:170-250; items are addressed through a small permutation (logical position ->
 //                      physical slot) so that a Brownian-bridge insertion or a pop never moves 16 KB items.
 //   SRA1 step ........ jitced_template.c:466-494;   error ratio / commit ... :502-536;   controller ... _jitcsde.py:569-630
@@ -18,7 +27,6 @@
 #pragma once
 
 #include "ensemble.cuh"
-#include "exact_div.cuh"
 #include "gauss.cuh"
 #include "mt19937.cuh"
 
@@ -26,6 +34,9 @@ namespace jsde {
 namespace wide {
 
 constexpr int WBLOCK = 256;
+constexpr int WWARPS = WBLOCK / 32;
+constexpr int TMAX = 8;       // trajectories per block: one warp each in the per-trajectory phases
+constexpr int TPAD = 8;       // row stride of the coupling stage buffer [units][TPAD] (64-byte rows)
 constexpr int CANDIDATES = MT_WORDS / 4;  // 156 per regenerated block
 constexpr int MAX_DEPTH = 64;
 
@@ -39,394 +50,533 @@ struct WideView {
 	int *order;        // [B][D]        logical position -> physical slot (a permutation; first q_count entries in use)
 	int *q_count;      // [B]
 	uint32_t *key;     // [B][624]      raw generator state (rk_state.key)
-	double *fifo;      // [B][3][156]   accepted pairs (x1, x2, r2) of the current block not yet consumed
-	int *fifo_rd, *fifo_cnt;  // [B]
+	int *pos;          // [B]           next unread word of the generator block (rk_state.pos; 624: regenerate first)
 	int *status;
 	unsigned long long *accepted, *rejected;
 	const double *par;
 	CallTotals *totals;
+	// scratch vectors [B][n], L2-resident: stage argument, Wiener increments DW/DZ of the current attempt, first drift
+	// (times h), proposal
+	double *arg, *sW, *sZ, *sF1, *sNY;
 };
 
-__global__ void k_wide_seed(uint32_t *key, int *fifo_rd, int *fifo_cnt, const uint32_t *seeds, int64_t B)
+__global__ void k_wide_seed(uint32_t *key, int *pos, const uint32_t *seeds, int64_t B)
 {
 	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= B)
 		return;
-	uint32_t *w = key + k * MT_WORDS;  // rk_seed (random_numbers.c:41-52); pos = 624 <=> nothing queued
+	uint32_t *w = key + k * MT_WORDS;  // rk_seed (random_numbers.c:41-52)
 	uint32_t v = seeds[k];
 	for (int i = 0; i < MT_WORDS; i++) {
 		w[i] = v;
 		v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i + 1u;
 	}
-	fifo_rd[k] = 0;
-	fifo_cnt[k] = 0;
+	pos[k] = MT_WORDS;
 }
 
-// The reference's batch twist (random_numbers.c:73-84) on a state held in shared memory; whole block must call.
-__device__ __forceinline__ void twist_block(uint32_t *key, int tid)
+// per-trajectory working set in shared memory
+struct TrajShared {
+	uint32_t key[MT_WORDS];
+	double qh[MAX_DEPTH];
+	int order[MAX_DEPTH];
+	double warp_max[WWARPS];
+	double t, dt, h;
+	int pos, count, cursor, status, running, last, accept, max_depth;
+	unsigned acc, rej, fresh;
+	int pad_;
+};
+
+// The reference's batch twist (random_numbers.c:73-84) by ONE warp on a state in shared memory.  Within a phase,
+// word i needs the old words i and i+1 (and a word the phase does not touch), so every 32-word strip is read, the warp
+// synchronised, and only then written.
+__device__ __forceinline__ void twist_warp(uint32_t *key, int lane)
 {
-	uint32_t v = 0;
-	if (tid < 227)
-		v = key[tid + 397] ^ mt_mix(key[tid], key[tid + 1]);
-	__syncthreads();
-	if (tid < 227)
-		key[tid] = v;
-	__syncthreads();
-	if (tid < 227)
-		v = key[tid] ^ mt_mix(key[tid + 227], key[tid + 228]);
-	__syncthreads();
-	if (tid < 227)
-		key[tid + 227] = v;
-	__syncthreads();
-	if (tid < 169)
-		v = key[tid + 227] ^ mt_mix(key[tid + 454], key[tid + 455]);
-	__syncthreads();
-	if (tid < 169)
-		key[tid + 454] = v;
-	__syncthreads();
-	if (tid == 0)
-		key[623] = key[396] ^ mt_mix(key[623], key[0]);
+	for (int i0 = 0; i0 < 227; i0 += 32) {  // kk < N-M: key[kk] = key[kk+M] ^ mix(key[kk], key[kk+1])
+		const int i = i0 + lane;
+		uint32_t v = 0;
+		if (i < 227)
+			v = mt_twist(key[i], key[i + 1], key[i + 397]);
+		__syncwarp();
+		if (i < 227)
+			key[i] = v;
+		__syncwarp();
+	}
+	for (int i0 = 227; i0 < 623; i0 += 32) {  // kk < N-1: key[kk] = key[kk+(M-N)] ^ mix(key[kk], key[kk+1])
+		const int i = i0 + lane;
+		uint32_t v = 0;
+		if (i < 623)
+			v = mt_twist(key[i], key[i + 1], key[i - 227]);
+		__syncwarp();
+		if (i < 623)
+			key[i] = v;
+		__syncwarp();
+	}
+	if (lane == 0)
+		key[623] = mt_twist(key[623], key[0], key[396]);
+	__syncwarp();
+}
+
+// c_i = sum_j AT[j][i] * (y_j - y_i) for the block's T trajectories; in: SC[j][tr] = y_j of trajectory tr, out (same
+// buffer): SC[i][tr] = c_i.  Whole block must call.
+template <int T, int UNITS>
+__device__ __forceinline__ void coupling_phase(const double *__restrict__ AT, double *SC, int tid)
+{
+	constexpr int IPT = (UNITS + WBLOCK - 1) / WBLOCK;  // rows per thread
+	constexpr int TP2 = (T + 1) / 2;
+	double yi[IPT][T], acc[IPT][T];
+	int row[IPT];
+#pragma unroll
+	for (int q = 0; q < IPT; q++) {
+		const int i = tid + q * WBLOCK;
+		row[q] = i < UNITS ? i : UNITS - 1;  // surplus threads recompute the last row and discard it
+#pragma unroll
+		for (int tr = 0; tr < T; tr++) {
+			yi[q][tr] = SC[row[q] * TPAD + tr];
+			acc[q][tr] = 0.0;
+		}
+	}
+#pragma unroll 4
+	for (int j = 0; j < UNITS; j++) {
+		double a[IPT];
+#pragma unroll
+		for (int q = 0; q < IPT; q++)
+			a[q] = __ldg(AT + (size_t)j * UNITS + row[q]);
+		double yj[2 * TP2];
+		const double2 *src = reinterpret_cast<const double2 *>(SC + j * TPAD);
+#pragma unroll
+		for (int u = 0; u < TP2; u++) {
+			const double2 v = src[u];  // same address for the whole warp: a broadcast
+			yj[2 * u] = v.x;
+			yj[2 * u + 1] = v.y;
+		}
+#pragma unroll
+		for (int q = 0; q < IPT; q++)
+#pragma unroll
+			for (int tr = 0; tr < T; tr++)
+				acc[q][tr] = acc[q][tr] + a[q] * (yj[tr] - yi[q][tr]);  // s += A*(Y[j]-Y[i]): three roundings, ascending j
+	}
+	__syncthreads();  // everybody has read the last y_j
+#pragma unroll
+	for (int q = 0; q < IPT; q++) {
+		const int i = tid + q * WBLOCK;
+		if (i < UNITS) {
+#pragma unroll
+			for (int tr = 0; tr < T; tr++)
+				SC[i * TPAD + tr] = acc[q][tr];
+		}
+	}
 	__syncthreads();
 }
 
-template <class Model>
-__global__ void __launch_bounds__(WBLOCK) k_wide_integrate(WideView e, Controller c, double target)
+// the block's live trajectories occupy the first `active` columns: run the variant unrolled for exactly that many
+template <int T, int UNITS>
+__device__ __forceinline__ void coupling_dispatch(int active, const double *__restrict__ AT, double *SC, int tid)
 {
+	switch (active) {
+	case 1: coupling_phase<1, UNITS>(AT, SC, tid); break;
+	case 2: if (T >= 2) coupling_phase<(T >= 2 ? 2 : 1), UNITS>(AT, SC, tid); break;
+	case 3: if (T >= 3) coupling_phase<(T >= 3 ? 3 : 1), UNITS>(AT, SC, tid); break;
+	case 4: if (T >= 4) coupling_phase<(T >= 4 ? 4 : 1), UNITS>(AT, SC, tid); break;
+	case 5: if (T >= 5) coupling_phase<(T >= 5 ? 5 : 1), UNITS>(AT, SC, tid); break;
+	case 6: if (T >= 6) coupling_phase<(T >= 6 ? 6 : 1), UNITS>(AT, SC, tid); break;
+	case 7: if (T >= 7) coupling_phase<(T >= 7 ? 7 : 1), UNITS>(AT, SC, tid); break;
+	case 8: if (T >= 8) coupling_phase<(T >= 8 ? 8 : 1), UNITS>(AT, SC, tid); break;
+	default: break;
+	}
+}
+
+template <class Model, int T>
+constexpr size_t wide_smem_bytes()
+{
+	return (size_t)(Model::UNITS > 0 ? Model::UNITS : 1) * TPAD * sizeof(double) + (size_t)T * sizeof(TrajShared);
+}
+
+template <class Model, int T>
+__global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Controller c, double target)
+{
+	static_assert(T >= 1 && T <= TMAX && T <= WWARPS, "one warp per trajectory");
 	constexpr int N = Model::N;
-	constexpr int CPT = (N + WBLOCK - 1) / WBLOCK;  // components per thread
-	__shared__ double Ysh[N], Ash[N];
-	__shared__ uint32_t key[MT_WORDS];
-	__shared__ double fx1[CANDIDATES], fx2[CANDIDATES], fr2[CANDIDATES];
-	__shared__ double s_qh[MAX_DEPTH];
-	__shared__ int s_order[MAX_DEPTH];
-	__shared__ int s_warp_count[WBLOCK / 32];
-	__shared__ double s_warp_max[WBLOCK / 32];
-	__shared__ double s_par[Model::NPAR > 0 ? Model::NPAR : 1];
+	constexpr int UNITS = Model::UNITS;  // the first UNITS components are densely coupled (0: no coupling term)
+	constexpr int CPT = (N + WBLOCK - 1) / WBLOCK;
+	extern __shared__ __align__(16) unsigned char wide_smem[];
+	double *SC = reinterpret_cast<double *>(wide_smem);
+	TrajShared *ts = reinterpret_cast<TrajShared *>(wide_smem + (size_t)(UNITS > 0 ? UNITS : 1) * TPAD * sizeof(double));
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int64_t b = blockIdx.x;
+	const int64_t b0 = (int64_t)blockIdx.x * T;
+	const int live = (int)min((int64_t)T, e.B - b0);  // trajectories of this block
 	const int D = e.D;
-	double *const qw = e.qw + b * D * 2 * N;
+	const unsigned lt = (1u << lane) - 1u;
 
-	// ---- load -----------------------------------------------------------------------------------------------------
-	double yv[CPT];
-#pragma unroll
-	for (int cc = 0; cc < CPT; cc++) {
-		const int i = cc * WBLOCK + tid;
-		yv[cc] = i < N ? e.y[b * N + i] : 0.0;
-		if (i < N)
-			Ysh[i] = yv[cc];
+	// ---- load: warp w owns trajectory w --------------------------------------------------------------------------
+	if (warp < T) {
+		TrajShared &S = ts[warp];
+		if (warp < live) {
+			const int64_t b = b0 + warp;
+			for (int i = lane; i < MT_WORDS; i += 32)
+				S.key[i] = e.key[b * MT_WORDS + i];
+			for (int d = lane; d < D; d += 32) {
+				S.qh[d] = e.qh[b * D + d];
+				S.order[d] = e.order[b * D + d];
+			}
+			if (lane == 0) {
+				S.t = e.t[b];
+				S.dt = e.dt[b];
+				S.pos = e.pos[b];
+				S.count = e.q_count[b];
+				int status = e.status[b];
+				if (status == TRAJ_MIN_STEP)
+					status = TRAJ_OK;  // the reference raises once per call and lets the caller carry on (_jitcsde.py:569-579)
+				S.status = status;
+				S.running = status == TRAJ_OK && !(S.t >= target);  // integrate() with nothing to do (:614)
+				S.acc = S.rej = S.fresh = 0;
+				S.max_depth = 0;
+				S.cursor = 0;
+				S.accept = 0;
+			}
+		} else if (lane == 0) {
+			S.running = 0;
+			S.accept = 0;
+			S.status = TRAJ_OK;
+			S.acc = S.rej = S.fresh = 0;
+			S.max_depth = 0;
+		}
 	}
-	for (int i = tid; i < MT_WORDS; i += WBLOCK)
-		key[i] = e.key[b * MT_WORDS + i];
-	int f_rd = e.fifo_rd[b], f_cnt = e.fifo_cnt[b];
-	for (int i = tid; i < f_cnt; i += WBLOCK) {
-		fx1[i] = e.fifo[(b * 3 + 0) * CANDIDATES + i];
-		fx2[i] = e.fifo[(b * 3 + 1) * CANDIDATES + i];
-		fr2[i] = e.fifo[(b * 3 + 2) * CANDIDATES + i];
-	}
-	if (tid < D) {
-		s_qh[tid] = e.qh[b * D + tid];
-		s_order[tid] = e.order[b * D + tid];
-	}
-	if (tid < Model::NPAR)
-		s_par[tid] = e.par[tid];
-	double t = e.t[b], dt = e.dt[b];
-	int count = e.q_count[b];
-	int status = e.status[b];
-	if (status == TRAJ_MIN_STEP)
-		status = TRAJ_OK;  // the reference raises once per call and lets the caller carry on (_jitcsde.py:569-579)
-	unsigned acc = 0, rej = 0, fresh = 0;
-	int max_depth = 0;
+	if (UNITS > 0)
+		for (int i = tid; i < UNITS * TPAD; i += WBLOCK)
+			SC[i] = 0.0;  // columns of absent trajectories stay zero
 	__syncthreads();
 
-	bool running = status == TRAJ_OK && !(t >= target);  // integrate() with nothing to do (:614)
-	while (running) {
-		// ---- one attempted step (identical control flow in every thread) ------------------------------------------
-		double h;
-		bool last = false;
-		if (t + dt < target)
-			h = dt;
-		else {
-			h = target - t;
-			last = true;
-		}
-		// noise memory: get_noise (template:204-250)
-		double W[CPT], Z[CPT];
-		bool started = false;
-		double need = h;
-		int cur = 0;
-		double hq = 0.0;
-		while (need != 0.0 && cur < count) {
-			const int s = s_order[cur];
-			hq = s_qh[s];
-			if (!(hq <= need))
-				break;
+	while (true) {
+		int any = 0;
 #pragma unroll
-			for (int cc = 0; cc < CPT; cc++) {
-				const int i = cc * WBLOCK + tid;
-				if (i < N) {
+		for (int tr = 0; tr < T; tr++)
+			any |= ts[tr].running;
+		if (!any)
+			break;
+
+		// ---- P1: per trajectory, one warp each: step size, noise memory (get_noise, template:204-250), draw ----------
+		if (warp < T && ts[warp].running) {
+			TrajShared &S = ts[warp];
+			const int64_t b = b0 + warp;
+			double *const qw = e.qw + b * D * 2 * N;
+			double *const sW = e.sW + b * N, *const sZ = e.sZ + b * N;
+			const double t = S.t, dt = S.dt;
+			double h;
+			bool last = false;
+			if (t + dt < target)
+				h = dt;
+			else {
+				h = target - t;
+				last = true;
+			}
+			int count = S.count, pos = S.pos;
+			bool started = false, overflow = false;
+			double need = h, hq = 0.0;
+			int cur = 0;
+			while (need != 0.0 && cur < count) {
+				const int s = S.order[cur];
+				hq = S.qh[s];
+				if (!(hq <= need))
+					break;
+				for (int i = lane; i < N; i += 32) {
 					const double w = qw[(s * 2 + 0) * N + i], z = qw[(s * 2 + 1) * N + i];
-					W[cc] = started ? W[cc] + w : w;
-					Z[cc] = started ? Z[cc] + z : z;
+					sW[i] = started ? sW[i] + w : w;
+					sZ[i] = started ? sZ[i] + z : z;
+				}
+				started = true;
+				need -= hq;
+				cur++;
+			}
+			__syncwarp();  // the draw below hands component k to an arbitrary lane: make the partial sums visible
+			if (need != 0.0) {
+				if (count >= D)
+					overflow = true;
+				else {
+					const bool bridging = cur < count;
+					double h_exc = 0.0, factor = 0.0, variance = need;  // append_noise (template:170-176)
+					if (bridging) {  // Brownian_bridge (template:178-202); hq is the too-long item's length
+						h_exc = hq - need;
+						factor = h_exc / hq;
+						variance = factor * need;
+					}
+					const double scale = sqrt(variance);
+					const int snew = S.order[count];  // a free physical slot
+					const int s1 = bridging ? S.order[cur] : snew;
+					// n pairs in stream order (get_gauss, template:145-154): pair k belongs to component k
+					int produced = 0;
+					while (produced < N) {
+						if (pos == MT_WORDS) {
+							twist_warp(S.key, lane);
+							pos = 0;
+						}
+						const int c0 = pos >> 2;
+						const int cand = c0 + lane;
+						bool ok = false;
+						double x1 = 0.0, x2 = 0.0, r2 = 0.0;
+						if (cand < CANDIDATES) {
+							uint4 w;
+							w.x = mt_temper(S.key[4 * cand]);
+							w.y = mt_temper(S.key[4 * cand + 1]);
+							w.z = mt_temper(S.key[4 * cand + 2]);
+							w.w = mt_temper(S.key[4 * cand + 3]);
+							ok = polar_candidate(w, x1, x2, r2);
+						}
+						const unsigned okm = __ballot_sync(0xffffffffu, ok);
+						const int navail = __popc(okm);
+						const int take = min(navail, N - produced);
+						const int rank = __popc(okm & lt);
+						if (ok && rank < take) {
+							const int k = produced + rank;
+							const double f = scale * polar_radius_factor(r2);
+							double gw = x1 * f, gz = x2 * f;
+							if (bridging) {
+								const double w1 = qw[(s1 * 2 + 0) * N + k], z1 = qw[(s1 * 2 + 1) * N + k];
+								const double w2 = gw + w1 * factor, z2 = gz + z1 * factor;
+								gw = w1 - w2;
+								gz = z1 - z2;
+								qw[(snew * 2 + 0) * N + k] = w2;
+								qw[(snew * 2 + 1) * N + k] = z2;
+								qw[(s1 * 2 + 0) * N + k] = gw;
+								qw[(s1 * 2 + 1) * N + k] = gz;
+							} else {
+								qw[(snew * 2 + 0) * N + k] = gw;
+								qw[(snew * 2 + 1) * N + k] = gz;
+							}
+							sW[k] = started ? sW[k] + gw : gw;
+							sZ[k] = started ? sZ[k] + gz : gz;
+						}
+						// candidates up to the last pair taken are consumed; rejected ones behind it would be rejected
+						// again by the next draw, so a fully used strip may be skipped as a whole
+						if (take == navail)
+							pos += 4 * min(32, CANDIDATES - c0);
+						else
+							pos += 4 * ((int)__fns(okm, 0, take) + 1);
+						produced += take;
+					}
+					__syncwarp();
+					if (lane == 0) {
+						if (bridging) {  // relink: the new second part goes right behind the cursor
+							for (int d = count; d > cur + 1; d--)
+								S.order[d] = S.order[d - 1];
+							S.order[cur + 1] = snew;
+							S.qh[s1] = need;
+							S.qh[snew] = h_exc;
+						} else
+							S.qh[snew] = need;
+					}
+					count++;
+					started = true;
+					cur++;
 				}
 			}
-			started = true;
-			need -= hq;
-			cur++;
+			if (!started && !overflow)
+				for (int i = lane; i < N; i += 32)
+					sW[i] = sZ[i] = 0.0;
+			if (lane == 0) {
+				S.h = h;
+				S.last = last;
+				S.pos = pos;
+				if (overflow) {
+					S.status = TRAJ_NOISE_OVERFLOW;
+					S.running = 0;
+				} else {
+					S.fresh += (count != S.count);
+					S.count = count;
+					S.cursor = cur;
+					S.max_depth = count > S.max_depth ? count : S.max_depth;
+				}
+			}
 		}
-		if (need != 0.0) {
-			if (count >= D) {
-				status = TRAJ_NOISE_OVERFLOW;
-				break;
+		__syncthreads();
+
+		// Trajectories that attempt a step in this round, as a bit mask (uniform over the block).  Their coupled
+		// components occupy the FIRST popc(mask) columns of the stage buffer, so that a block whose trajectories have
+		// partly finished (step counts differ by a factor of three across an ensemble) only pays for the live ones.
+		unsigned mask = 0;
+#pragma unroll
+		for (int tr = 0; tr < T; tr++)
+			mask |= ts[tr].running ? 1u << tr : 0u;
+		const int active = __popc(mask);
+
+		// ---- P0: stage the coupled part of every running trajectory's state -----------------------------------------
+		if (UNITS > 0) {
+			int col = 0;
+			for (unsigned m = mask; m; m &= m - 1, col++) {
+				const double *Y = e.y + (b0 + (__ffs(m) - 1)) * N;
+				for (int i = tid; i < UNITS; i += WBLOCK)
+					SC[i * TPAD + col] = Y[i];
 			}
-			const bool bridging = cur < count;
-			double h_exc = 0.0, factor = 0.0, scale;
-			if (bridging) {  // Brownian_bridge (template:178-202); hq is the too-long item's length
-				h_exc = hq - need;
-				factor = h_exc / hq;
-				scale = sqrt(factor * need);
-			} else  // append_noise (template:170-176)
-				scale = sqrt(need);
-			// ---- draw n pairs in stream order (get_gauss, template:145-154) ----------------------------------------
-			double gW[CPT], gZ[CPT];
-			int produced = 0;
-			while (produced < N) {
-				if (f_rd == f_cnt) {  // nothing queued: regenerate the generator block and form its 156 candidates
-					__syncthreads();  // everybody is done reading the old queue
-					twist_block(key, tid);
-					bool ok = false;
-					double x1 = 0.0, x2 = 0.0, r2 = 0.0;
-					if (tid < CANDIDATES) {
-						uint4 w;
-						w.x = mt_temper(key[4 * tid]);
-						w.y = mt_temper(key[4 * tid + 1]);
-						w.z = mt_temper(key[4 * tid + 2]);
-						w.w = mt_temper(key[4 * tid + 3]);
-						ok = polar_candidate(w, x1, x2, r2);
-					}
-					const unsigned okm = __ballot_sync(0xffffffffu, ok);
-					if (lane == 0)
-						s_warp_count[warp] = __popc(okm);
-					__syncthreads();
-					int base = 0, total = 0;
+			__syncthreads();
+		}
+
+		for (int stage = 0; stage < 2; stage++) {
+			if (UNITS > 0)
+				coupling_dispatch<T, UNITS>(active, Model::coupling_table(), SC, tid);
+			if (stage == 0) {
+				// ---- P3: first stage (template:468-481) ----------------------------------------------------------------
+				int col = 0;
+				for (unsigned m = mask; m; m &= m - 1, col++) {
+					const int tr = __ffs(m) - 1;
+					const int64_t b = b0 + tr;
+					const double *Y = e.y + b * N;
+					const double t = ts[tr].t, h = ts[tr].h;
 #pragma unroll
-					for (int w = 0; w < WBLOCK / 32; w++) {
-						const int cw = s_warp_count[w];
-						base += w < warp ? cw : 0;
-						total += cw;
-					}
-					if (ok) {
-						const int at = base + __popc(okm & ((1u << lane) - 1u));
-						fx1[at] = x1;
-						fx2[at] = x2;
-						fr2[at] = r2;
-					}
-					f_rd = 0;
-					f_cnt = total;
-					__syncthreads();
-				}
-				const int take = min(f_cnt - f_rd, N - produced);
-#pragma unroll
-				for (int cc = 0; cc < CPT; cc++) {
-					const int i = cc * WBLOCK + tid;
-					if (i >= produced && i < produced + take) {  // pair (i - produced) of this batch is component i's
-						const int at = f_rd + (i - produced);
-						const double r2 = fr2[at];
-						const double f = scale * polar_radius_factor(r2);
-						gW[cc] = fx1[at] * f;
-						gZ[cc] = fx2[at] * f;
+					for (int cc = 0; cc < CPT; cc++) {
+						const int i = cc * WBLOCK + tid;
+						if (i < N) {
+							const double cs = (UNITS > 0 && i < UNITS) ? SC[i * TPAD + col] : 0.0;
+							const double I10 = (e.sW[b * N + i] + e.sZ[b * N + i] * (1. / 1.7320508075688772)) * (h / 2.);
+							const double fh1 = Model::drift_local(i, t, Y, e.par, cs) * h;
+							const double g1 = Model::diffusion_component(i, t + h, Y, e.par);
+							const double a = Y[i] + 0.75 * fh1 + 0.5 * g1 * I10 / h;
+							e.sF1[b * N + i] = fh1;
+							e.arg[b * N + i] = a;
+							if (UNITS > 0 && i < UNITS)
+								SC[i * TPAD + col] = a;  // this thread's own cell: read above, rewritten here
+						}
 					}
 				}
-				f_rd += take;
-				produced += take;
-			}
-			fresh++;
-			const int snew = s_order[count];  // a free physical slot
-			if (bridging) {
-				const int s1 = s_order[cur];
-				__syncthreads();
-				if (tid == 0) {  // relink: the new second part goes right behind the cursor
-					for (int d = count; d > cur + 1; d--)
-						s_order[d] = s_order[d - 1];
-					s_order[cur + 1] = snew;
-					s_qh[s1] = need;
-					s_qh[snew] = h_exc;
-				}
-#pragma unroll
-				for (int cc = 0; cc < CPT; cc++) {
-					const int i = cc * WBLOCK + tid;
-					if (i < N) {
-						const double w1 = qw[(s1 * 2 + 0) * N + i], z1 = qw[(s1 * 2 + 1) * N + i];
-						const double w2 = gW[cc] + w1 * factor, z2 = gZ[cc] + z1 * factor;
-						gW[cc] = w1 - w2;
-						gZ[cc] = z1 - z2;
-						qw[(snew * 2 + 0) * N + i] = w2;
-						qw[(snew * 2 + 1) * N + i] = z2;
-						qw[(s1 * 2 + 0) * N + i] = gW[cc];
-						qw[(s1 * 2 + 1) * N + i] = gZ[cc];
-					}
-				}
-				__syncthreads();
 			} else {
-				if (tid == 0)
-					s_qh[snew] = need;
+				// ---- P5: second stage, proposal, error ratio (template:482-526) -----------------------------------------
+				int col = 0;
+				for (unsigned m = mask; m; m &= m - 1, col++) {
+					const int tr = __ffs(m) - 1;
+					const int64_t b = b0 + tr;
+					const double *Y = e.y + b * N, *A = e.arg + b * N;
+					const double t = ts[tr].t, h = ts[tr].h;
+					const double t_mid = t + 0.75 * h;
+					double worst = 0.0;
 #pragma unroll
-				for (int cc = 0; cc < CPT; cc++) {
-					const int i = cc * WBLOCK + tid;
-					if (i < N) {
-						qw[(snew * 2 + 0) * N + i] = gW[cc];
-						qw[(snew * 2 + 1) * N + i] = gZ[cc];
+					for (int cc = 0; cc < CPT; cc++) {
+						const int i = cc * WBLOCK + tid;
+						if (i < N) {
+							const double cs = (UNITS > 0 && i < UNITS) ? SC[i * TPAD + col] : 0.0;
+							const double W = e.sW[b * N + i];
+							const double I10 = (W + e.sZ[b * N + i] * (1. / 1.7320508075688772)) * (h / 2.);
+							const double fh1 = e.sF1[b * N + i];
+							const double fh2 = Model::drift_local(i, t_mid, A, e.par, cs) * h;
+							const double g1 = Model::diffusion_component(i, t + h, Y, e.par);
+							const double g2 = Model::diffusion_component(i, t, Y, e.par);
+							const double E_N = I10 / h * (g2 - g1);
+							const double ny = Y[i] + E_N + (1. / 3.) * (fh1 + 2 * fh2) + W * g1;
+							const double E_D = (fh2 - fh1) / 6;
+							const double er = fabs(E_D) + fabs(E_N);
+							e.sNY[b * N + i] = ny;
+							const double tol = c.atol + c.rtol * fabs(ny);  // get_p (template:502-526)
+							if (er != 0.0 || tol != 0.0) {
+								const double x = er / tol;
+								if (x > worst)
+									worst = x;
+							}
+						}
 					}
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1) {  // maximum: exact and order-independent
+						const double other = __shfl_xor_sync(0xffffffffu, worst, o);
+						worst = other > worst ? other : worst;
+					}
+					if (lane == 0)
+						ts[tr].warp_max[warp] = worst;
 				}
-				__syncthreads();
 			}
-			count++;
-#pragma unroll
-			for (int cc = 0; cc < CPT; cc++) {
-				W[cc] = started ? W[cc] + gW[cc] : gW[cc];
-				Z[cc] = started ? Z[cc] + gZ[cc] : gZ[cc];
-			}
-			started = true;
-			cur++;
+			__syncthreads();
 		}
-		if (!started) {
-#pragma unroll
-			for (int cc = 0; cc < CPT; cc++)
-				W[cc] = Z[cc] = 0.0;
-		}
-		const int cursor = cur;
-		max_depth = count > max_depth ? count : max_depth;
 
-		// ---- SRA1 (template:468-494) -------------------------------------------------------------------------------
-		double fh1[CPT], fh2[CPT], g1[CPT], ny[CPT], er[CPT], I10[CPT];
+		// ---- P6: controller (_jitcsde.py:581-595) and commit bookkeeping, one warp per trajectory ----------------------
+		if (warp < T && ts[warp].running) {
+			TrajShared &S = ts[warp];
+			double p = 0.0;
 #pragma unroll
-		for (int cc = 0; cc < CPT; cc++) {
-			const int i = cc * WBLOCK + tid;
-			if (i < N) {
-				I10[cc] = (W[cc] + Z[cc] * (1. / 1.7320508075688772)) * (h / 2.);
-				fh1[cc] = Model::drift_component(i, t, Ysh, s_par) * h;
-				g1[cc] = Model::diffusion_component(i, t + h, Ysh, s_par);
-				Ash[i] = yv[cc] + 0.75 * fh1[cc] + 0.5 * g1[cc] * I10[cc] / h;
+			for (int w = 0; w < WWARPS; w++)
+				p = S.warp_max[w] > p ? S.warp_max[w] : p;
+			const double h = S.h;
+			double dt = S.dt;
+			const bool rejecting = p > c.dec_thr;
+			const bool growing = !rejecting && p <= c.inc_thr;
+			double pw = 0.0;
+			if ((rejecting && p <= 1.7976931348623157e308) || (growing && p != 0.0))
+				pw = jsde_pow(p, rejecting ? c.shrink_exp : c.grow_exp);
+			__syncwarp();
+			if (lane == 0) {
+				if (rejecting) {
+					const double shrink = c.safety * pw;
+					dt = h * (c.min_factor > shrink ? c.min_factor : shrink);
+					S.rej++;
+					S.accept = 0;
+					if (dt < c.min_step) {
+						S.status = TRAJ_MIN_STEP;
+						S.running = 0;
+					}
+				} else {
+					if (growing) {
+						const double factor = (p != 0.0) ? c.safety * pw : c.max_factor;
+						const double sug = h * (c.max_factor < factor ? c.max_factor : factor);
+						const double capped = c.max_step < sug ? c.max_step : sug;
+						dt = capped > dt ? capped : dt;
+					}
+					// accept_step (template:528-536): drop the consumed items — rotate their slots behind the ones in use
+					const int cursor = S.cursor, count = S.count;
+					if (cursor > 0) {
+						int freed[MAX_DEPTH];
+						for (int d = 0; d < cursor; d++)
+							freed[d] = S.order[d];
+						for (int d = cursor; d < count; d++)
+							S.order[d - cursor] = S.order[d];
+						for (int d = 0; d < cursor; d++)
+							S.order[count - cursor + d] = freed[d];
+					}
+					S.count = count - cursor;
+					S.t = S.t + h;
+					S.acc++;
+					S.accept = 1;
+					if (S.last)
+						S.running = 0;
+				}
+				S.dt = dt;
 			}
 		}
 		__syncthreads();
-		double worst = 0.0;
-		const double t_mid = t + 0.75 * h;
-#pragma unroll
-		for (int cc = 0; cc < CPT; cc++) {
-			const int i = cc * WBLOCK + tid;
-			if (i < N) {
-				fh2[cc] = Model::drift_component(i, t_mid, Ash, s_par) * h;
-				const double g2 = Model::diffusion_component(i, t, Ysh, s_par);
-				const double E_N = I10[cc] / h * (g2 - g1[cc]);
-				ny[cc] = yv[cc] + E_N + (1. / 3.) * (fh1[cc] + 2 * fh2[cc]) + W[cc] * g1[cc];
-				const double E_D = (fh2[cc] - fh1[cc]) / 6;
-				er[cc] = fabs(E_D) + fabs(E_N);
-				const double tol = c.atol + c.rtol * fabs(ny[cc]);  // get_p (template:502-526)
-				if (er[cc] != 0.0 || tol != 0.0) {
-					const double x = er[cc] / tol;
-					if (x > worst)
-						worst = x;
-				}
-			}
-		}
-		// block maximum (exact, order-independent)
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) {
-			const double other = __shfl_xor_sync(0xffffffffu, worst, o);
-			worst = other > worst ? other : worst;
-		}
-		if (lane == 0)
-			s_warp_max[warp] = worst;
-		__syncthreads();
-		double p = 0.0;
-#pragma unroll
-		for (int w = 0; w < WBLOCK / 32; w++)
-			p = s_warp_max[w] > p ? s_warp_max[w] : p;
 
-		// ---- controller (_jitcsde.py:581-595), evaluated identically by every thread -------------------------------
-		const bool rejecting = p > c.dec_thr;
-		const bool growing = !rejecting && p <= c.inc_thr;
-		double pw = 0.0;
-		if ((rejecting && p <= 1.7976931348623157e308) || (growing && p != 0.0))
-			pw = jsde_pow(p, rejecting ? c.shrink_exp : c.grow_exp);
-		if (rejecting) {
-			const double shrink = c.safety * pw;
-			dt = h * (c.min_factor > shrink ? c.min_factor : shrink);
-			rej++;
-			if (dt < c.min_step) {
-				status = TRAJ_MIN_STEP;
-				running = false;
-			}
-		} else {
-			if (growing) {
-				const double factor = (p != 0.0) ? c.safety * pw : c.max_factor;
-				const double sug = h * (c.max_factor < factor ? c.max_factor : factor);
-				const double capped = c.max_step < sug ? c.max_step : sug;
-				dt = capped > dt ? capped : dt;
-			}
-			// accept_step (template:528-536)
-#pragma unroll
-			for (int cc = 0; cc < CPT; cc++) {
-				const int i = cc * WBLOCK + tid;
-				if (i < N) {
-					yv[cc] = ny[cc];
-					Ysh[i] = ny[cc];
-				}
-			}
-			t = t + h;
-			if (cursor > 0 && tid == 0) {  // drop the consumed items: rotate their slots behind the ones still in use
-				int freed[MAX_DEPTH];
-				for (int d = 0; d < cursor; d++)
-					freed[d] = s_order[d];
-				for (int d = cursor; d < count; d++)
-					s_order[d - cursor] = s_order[d];
-				for (int d = 0; d < cursor; d++)
-					s_order[count - cursor + d] = freed[d];
-			}
-			count -= cursor;
-			acc++;
-			if (last)
-				running = false;
+		// ---- P7: commit the accepted proposals ---------------------------------------------------------------------------
+		for (int tr = 0; tr < T; tr++) {
+			if (!ts[tr].accept)
+				continue;
+			const int64_t b = b0 + tr;
+			for (int i = tid; i < N; i += WBLOCK)
+				e.y[b * N + i] = e.sNY[b * N + i];
 		}
+		__syncthreads();
+		if (tid < T)
+			ts[tid].accept = 0;
 		__syncthreads();
 	}
 
 	// ---- store ----------------------------------------------------------------------------------------------------
-	__syncthreads();
-#pragma unroll
-	for (int cc = 0; cc < CPT; cc++) {
-		const int i = cc * WBLOCK + tid;
-		if (i < N)
-			e.y[b * N + i] = yv[cc];
-	}
-	for (int i = tid; i < MT_WORDS; i += WBLOCK)
-		e.key[b * MT_WORDS + i] = key[i];
-	for (int i = tid; i < f_cnt - f_rd; i += WBLOCK) {  // queue normalised to start at 0
-		e.fifo[(b * 3 + 0) * CANDIDATES + i] = fx1[f_rd + i];
-		e.fifo[(b * 3 + 1) * CANDIDATES + i] = fx2[f_rd + i];
-		e.fifo[(b * 3 + 2) * CANDIDATES + i] = fr2[f_rd + i];
-	}
-	if (tid < D) {
-		e.qh[b * D + tid] = s_qh[tid];
-		e.order[b * D + tid] = s_order[tid];
-	}
-	if (tid == 0) {
-		e.t[b] = t;
-		e.dt[b] = dt;
-		e.q_count[b] = count;
-		e.fifo_rd[b] = 0;
-		e.fifo_cnt[b] = f_cnt - f_rd;
-		e.status[b] = status;
-		e.accepted[b] += acc;
-		e.rejected[b] += rej;
-		if (acc) atomicAdd(&e.totals->accepted, (unsigned long long)acc);
-		if (rej) atomicAdd(&e.totals->rejected, (unsigned long long)rej);
-		if (fresh) atomicAdd(&e.totals->fresh_draws, (unsigned long long)fresh);
-		if (status == TRAJ_MIN_STEP) atomicAdd((unsigned long long *)&e.totals->n_min_step, 1ull);
-		if (status == TRAJ_NOISE_OVERFLOW) atomicAdd((unsigned long long *)&e.totals->n_overflow, 1ull);
-		atomicMax(&e.totals->max_depth, max_depth);
+	if (warp < live) {
+		TrajShared &S = ts[warp];
+		const int64_t b = b0 + warp;
+		for (int i = lane; i < MT_WORDS; i += 32)
+			e.key[b * MT_WORDS + i] = S.key[i];
+		for (int d = lane; d < D; d += 32) {
+			e.qh[b * D + d] = S.qh[d];
+			e.order[b * D + d] = S.order[d];
+		}
+		if (lane == 0) {
+			e.t[b] = S.t;
+			e.dt[b] = S.dt;
+			e.pos[b] = S.pos;
+			e.q_count[b] = S.count;
+			e.status[b] = S.status;
+			e.accepted[b] += S.acc;
+			e.rejected[b] += S.rej;
+			if (S.acc) atomicAdd(&e.totals->accepted, (unsigned long long)S.acc);
+			if (S.rej) atomicAdd(&e.totals->rejected, (unsigned long long)S.rej);
+			if (S.fresh) atomicAdd(&e.totals->fresh_draws, (unsigned long long)S.fresh);
+			if (S.status == TRAJ_MIN_STEP) atomicAdd((unsigned long long *)&e.totals->n_min_step, 1ull);
+			if (S.status == TRAJ_NOISE_OVERFLOW) atomicAdd((unsigned long long *)&e.totals->n_overflow, 1ull);
+			atomicMax(&e.totals->max_depth, S.max_depth);
+		}
 	}
 }
 

@@ -70,20 +70,12 @@ def fhn_network(units: int, name: str, seed: int = 7) -> ModelSpec:
 #endif
 #define FHN_UNITS {units}
 JSDE_MODEL_CONST double FHN_AT[FHN_UNITS * FHN_UNITS] = {{{table}}};
-JSDE_MODEL_FN double fhn_drift(int i, const double *Y)
-{{
-	if (i < FHN_UNITS) {{
-		double s = 0.0;
-		for (int j = 0; j < FHN_UNITS; j++)
-			s += FHN_AT[j * FHN_UNITS + i] * (Y[j] - Y[i]);
-		return Y[i] - Y[i] * Y[i] * Y[i] / 3.0 - Y[FHN_UNITS + i] + 0.5 + (1.0 / FHN_UNITS) * s;
-	}}
-	const int u = i - FHN_UNITS;
-	return 0.08 * (Y[u] + 0.7 - 0.8 * Y[i]);
-}}
 """
+	f_component = ("(i < FHN_UNITS ? y(i) - y(i) * y(i) * y(i) / 3.0 - y(FHN_UNITS + i) + 0.5 + (1.0 / FHN_UNITS) * coupling"
+		" : 0.08 * (y(i - FHN_UNITS) + 0.7 - 0.8 * y(i)))")
 	return ModelSpec(name, 2 * units, True, (), (), preamble=preamble,
-		f_component="fhn_drift(i, Y)", g_component="(i < FHN_UNITS ? 0.05 : 0.0)")
+		f_component=f_component, g_component="(i < FHN_UNITS ? 0.05 : 0.0)",
+		coupling_units=units, coupling_table="FHN_AT")
 
 
 #: small network for the parity tests of the wide (block-per-trajectory) kernel

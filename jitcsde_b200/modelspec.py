@@ -52,6 +52,12 @@ class ModelSpec:
 	# over i.  `preamble` may use JSDE_MODEL_FN (function qualifier) and JSDE_MODEL_CONST (table qualifier).
 	f_component: str = ""
 	g_component: str = ""
+	# Dense linear coupling applied across the ensemble batch: `f_component` may use the word `coupling`, which stands
+	# for  sum_j TABLE[j*units + i] * (y(j) - y(i))  (j ascending, separately rounded) when i < coupling_units and for
+	# 0.0 otherwise; TABLE (the transposed coupling matrix) is defined in `preamble`.  The GPU evaluates the sums of
+	# all trajectories of a thread block together (csrc/wide.cuh); the oracle's C gets a plain loop.
+	coupling_units: int = 0
+	coupling_table: str = ""
 
 	@property
 	def wide(self) -> bool:
@@ -62,6 +68,22 @@ class ModelSpec:
 			assert self.g_component, "wide models need g_component too"
 			assert self.additive, "wide models are implemented for additive noise (SRA) only"
 			assert self.jump is None
+			if self.coupling_units:
+				assert self.coupling_table and 0 < self.coupling_units <= self.n
+				u, tab = self.coupling_units, self.coupling_table
+				object.__setattr__(self, "preamble", self.preamble + f"""
+#ifndef JSDE_DEVICE_COUPLING  /* host/oracle: the coupling term as a plain loop; the CUDA path batches it over trajectories */
+JSDE_MODEL_FN double jsde_coupling_sum(int i, const double *Y)
+{{
+	if (i >= {u}) return 0.0;
+	double s = 0.0;
+	for (int j = 0; j < {u}; j++)
+		s += {tab}[j * {u} + i] * (Y[j] - Y[i]);
+	return s;
+}}
+#define coupling jsde_coupling_sum(i, Y)
+#endif
+""")
 			object.__setattr__(self, "f_body", f"for (int i = 0; i < {self.n}; i++) set_drift(i, {self.f_component});\n")
 			object.__setattr__(self, "g_body", f"for (int i = 0; i < {self.n}; i++) set_diffusion(i, {self.g_component});\n")
 		if not self.f_body:
@@ -72,7 +94,8 @@ class ModelSpec:
 	def digest(self) -> str:
 		h = hashlib.sha256()
 		for part in (self.name, str(self.n), str(self.additive), *self.f, "|", *self.g, "|", *self.control_pars,
-				"|", *(self.jump.amp if self.jump else ()), "|", self.preamble, self.f_body, self.g_body, self.f_component, self.g_component):
+				"|", *(self.jump.amp if self.jump else ()), "|", self.preamble, self.f_body, self.g_body, self.f_component, self.g_component,
+				str(self.coupling_units), self.coupling_table):
 			h.update(part.encode())
 			h.update(b"\0")
 		return h.hexdigest()[:16]

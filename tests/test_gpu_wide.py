@@ -21,8 +21,10 @@ def run(spec, B, T, **ctrl):
 	return E, E.integrate(T), y0
 
 
-def test_small_network_vs_oracle():
-	spec = models.fhn_small  # n = 48: one component per thread, most threads idle except in the generator
+@pytest.mark.parametrize("tpb", [1, 2, 4, 7, 8])
+def test_small_network_vs_oracle(monkeypatch, tpb):
+	monkeypatch.setenv("JSDE_WIDE_TPB", str(tpb))  # trajectories per thread block (37 = 4*8 + 5: a ragged last block)
+	spec = models.fhn_small  # n = 48, 24 coupled units
 	B, T = 37, 3.0
 	E, stats, y0 = run(spec, B, T)
 	ref = port.run_ensemble(spec, y0, sharding.global_seeds(0, B), 0.0, T)
@@ -40,9 +42,11 @@ def test_small_network_vs_oracle():
 	assert not np.array_equal(E.get_state(), ref2["y"]) or True  # (one-shot to 4.0 differs: the step at t=3 was truncated)
 
 
-def test_config5_network_n1000_vs_oracle():
-	spec = models.fhn_1000()  # 500 units x (v, w), dense 500x500 coupling, 4 components per thread
-	B, T = 6, 0.15
+@pytest.mark.parametrize("tpb,B", [(7, 9), (2, 3)])
+def test_config5_network_n1000_vs_oracle(monkeypatch, tpb, B):
+	monkeypatch.setenv("JSDE_WIDE_TPB", str(tpb))
+	spec = models.fhn_1000()  # 500 units x (v, w), dense 500x500 coupling batched over the block's trajectories
+	T = 0.15
 	E, stats, y0 = run(spec, B, T)
 	ref = port.run_ensemble(spec, y0, sharding.global_seeds(0, B), 0.0, T)
 	assert_bits_equal(E.get_state(), ref["y"], "states")
