@@ -11,8 +11,9 @@
 //     scheduler interleaves them (round 1, profiles/r01_v12_*: a warp that did both issued on 60 % of cycles with
 //     2.2 cycles of fixed-latency stall per instruction and only 16 warps per SM because of 128 registers/thread);
 //   * `setmaxnreg` moves registers from the producers to the consumers: 24 warps per SM instead of 16;
-//   * the generator's HBM latency is hidden by the other warps and one slot of register prefetch — no prediction of
-//     the next refill, no staging area.
+//   * the generator's HBM latency is hidden by the other warps and by staging the state words of the next two slots
+//     with cp.async while one slot is processed — no prediction of the next refill (measured: an additional L2
+//     prefetch one round ahead, or a deeper staging pipeline, changes nothing).
 //
 // Protocol (per pair, one named barrier of 64 threads per round, control words double-buffered by round parity):
 //
@@ -43,13 +44,14 @@ constexpr int DUO_BLOCK = 64 * DUO_PAIRS;
 #ifndef JSDE_DUO_PRODUCER_REGS
 #define JSDE_DUO_PRODUCER_REGS 56
 #endif
+#ifndef JSDE_DUO_STAGE_AHEAD
+#define JSDE_DUO_STAGE_AHEAD 2  // slots whose generator words are in flight (cp.async) ahead of the one being processed
+#endif
 
 __device__ __forceinline__ void pair_barrier(int pair)
 {
 	asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");  // barrier 0 is __syncthreads()
 }
-
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // glibc's log table {invc, logc}[128] and pow tables invc[128], logc[128], logctail[128], exp_tab[256] in shared memory:
 // a lane-per-trajectory caller looks up 32 different entries at once.  Whole block must call.
@@ -73,7 +75,7 @@ struct PairLayout {
 	static constexpr int CAP = WarpRng<N>::CAP;
 	static constexpr int FIFO_DOUBLES = 3 * CAP * RNG_STRIDE;
 	// FIFOs x1, x2, r2 [CAP][RNG_STRIDE] | popped[2][32] u32 | mask[2] u32 | order[32] u8 | stage[3][4][18] uint4
-	static constexpr int STAGE_DEPTH = 3;  // slots whose generator words are in flight (cp.async) or being processed
+	static constexpr int STAGE_DEPTH = JSDE_DUO_STAGE_AHEAD + 1;  // slots whose generator words are in flight (cp.async) or being processed
 	static constexpr int STAGE_OFFSET = (FIFO_DOUBLES + 32 + 1 + 4 + 1) & ~1;  // 16-byte aligned
 	static constexpr int DOUBLES = STAGE_OFFSET + STAGE_DEPTH * 4 * RNG_STAGE_CHUNKS * 2;
 	static __device__ __forceinline__ uint4 *stage(double *base, int buf, int g) { return reinterpret_cast<uint4 *>(base + STAGE_OFFSET) + (buf * 4 + g) * RNG_STAGE_CHUNKS; }
@@ -214,12 +216,13 @@ struct PairProducer {
 			L::order(base)[below] = (unsigned char)lane;  // compacted list of the lanes to serve
 		__syncwarp();
 		int mine = 0;
-		stage_slot(0, nserved, g, j);
-		stage_slot(1, nserved, g, j);
+#pragma unroll
+		for (int s = 0; s < JSDE_DUO_STAGE_AHEAD; s++)
+			stage_slot(s, nserved, g, j);
 #pragma unroll 1
 		for (int s = 0; s < slots; s++) {
-			stage_slot(s + 2, nserved, g, j);  // reuses the buffer read in iteration s-1 (the ballot below ordered those reads)
-			asm volatile("cp.async.wait_group 2;" ::: "memory");
+			stage_slot(s + JSDE_DUO_STAGE_AHEAD, nserved, g, j);  // reuses the buffer read in iteration s-1 (the ballot below ordered those reads)
+			asm volatile("cp.async.wait_group %0;" ::"n"(JSDE_DUO_STAGE_AHEAD) : "memory");
 			__syncwarp();
 			const int rank = 4 * s + g;
 			const bool have = rank < nserved;
@@ -283,16 +286,6 @@ struct PairProducer {
 			const bool wants = usable && ((act >> lane) & 1u);
 			while (__ballot_sync(full, wants && lvl < 2 * N))
 				refill(__ballot_sync(full, wants && lvl <= CAP - RNG_GROUP));
-			// The consumer will most likely pop N pairs in this round; trajectories that then fall below 2N are served
-			// right after the next barrier.  Pull their next state and tap words (chunks c..c+8, c+99..c+107) into L2
-			// now — a wrong guess costs four prefetches.
-			if (wants && lvl - N < 2 * N) {
-				const uint4 *ST = S0 + lane * MT_CHUNKS;
-				prefetch_l2(ST + chunk);
-				prefetch_l2(ST + mt_wrap(chunk + 8));
-				prefetch_l2(ST + mt_wrap(chunk + 99));
-				prefetch_l2(ST + mt_wrap(chunk + 107));
-			}
 		}
 	}
 };

@@ -9,6 +9,10 @@
 // average).  Here all global accesses to the generator state are 128-byte contiguous per trajectory, every candidate
 // is computed exactly once, and the expensive log/div/sqrt run later, convergent, when a lane consumes a pair.
 //
+// This class serves the single-step kernels (get_next_step, pin_noise, the generator debug stream), where the warp
+// that consumes the pairs also produces them.  The fused integrate kernel splits the two roles between warps
+// (duo.cuh) and shares this file's vocabulary (slot layout, FIFO row stride, spill format).
+//
 // One refill step ("op"): lane l serves trajectory T = (g-th trajectory that has room, g = l/8), candidate j = l%8:
 //   loads state chunk c+j and tap chunk c+99+j of T (c = T's stream position), exchanges the two edge words with its
 //   neighbour by shuffle, writes the regenerated chunk back (mt19937.cuh explains the incremental twist), tempers,
@@ -34,27 +38,23 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-constexpr int RNG_STAGE_ENTRIES = 16;  // trajectories whose next state words are staged one phase ahead
-constexpr int RNG_STAGE_CHUNKS = 18;   // per entry: chunks c..c+8 and c+99..c+107
+constexpr int RNG_STAGE_CHUNKS = 18;   // staged words of one trajectory and slot (duo.cuh): chunks c..c+8 and c+99..c+107
 
 template <int N>
 struct WarpRng {
 	// room for the pairs left over below two draws' need (2N-1) plus a full group: the producer warps of the fused
 	// integrate kernel (duo.cuh) keep every trajectory one draw ahead of its consumer; the spill format is shared
 	static constexpr int CAP = 2 * N - 1 + RNG_GROUP;
-	static constexpr int FIFO_DOUBLES = (3 * CAP * RNG_STRIDE + 1) & ~1;  // even: keeps the staging area 16-byte aligned
-	// FIFOs | order_()[32] bytes | stage_of_()[32] bytes | staged state words
-	static constexpr int SMEM_DOUBLES_PER_WARP = FIFO_DOUBLES + 4 + 4 + RNG_STAGE_ENTRIES * RNG_STAGE_CHUNKS * 2;
+	static constexpr int FIFO_DOUBLES = (3 * CAP * RNG_STRIDE + 1) & ~1;
+	// FIFOs | order_()[32] bytes
+	static constexpr int SMEM_DOUBLES_PER_WARP = FIFO_DOUBLES + 4;
 
 	double *fx1;              // this warp's shared memory: FIFO arrays x1, x2, r2, each [CAP][RNG_STRIDE], then ...
 	const double *log_tab;    // block-shared copy of glibc's log table {invc, logc}[128]
 	__device__ __forceinline__ double *fx2_() const { return fx1 + CAP * RNG_STRIDE; }
 	__device__ __forceinline__ double *fr2_() const { return fx1 + 2 * CAP * RNG_STRIDE; }
-	// ... order_()[32]: scratch list of lanes being served; stage_of_()[32]: staging entry of each lane's trajectory (0xFF:
-	// none); stage[RNG_STAGE_ENTRIES][RNG_STAGE_CHUNKS]: staged state words
+	// ... order_()[32]: scratch list of lanes being served
 	__device__ __forceinline__ unsigned char *order_() const { return reinterpret_cast<unsigned char *>(fx1 + FIFO_DOUBLES); }
-	__device__ __forceinline__ unsigned char *stage_of_() const { return reinterpret_cast<unsigned char *>(fx1 + FIFO_DOUBLES + 4); }
-	__device__ __forceinline__ uint4 *stage_() const { return reinterpret_cast<uint4 *>(fx1 + FIFO_DOUBLES + 8); }
 	uint4 *S0;                // generator record of the warp's lane-0 trajectory
 	int lane;
 	int rd, lvl, chunk;       // this lane's FIFO read slot / fill level, its trajectory's next chunk
@@ -71,7 +71,6 @@ struct WarpRng {
 	{
 		rd = 0;
 		lvl = 0;
-		stage_of_()[lane] = 0xFF;
 		if (usable) {
 			lvl = levels[k];
 			chunk = chunks[k];
@@ -86,7 +85,6 @@ struct WarpRng {
 
 	__device__ __forceinline__ void store(double *spill, int *levels, int *chunks, int64_t B, int64_t k) const
 	{
-		cp_async_wait_all();  // staged words are simply dropped; the copies must not outlive the block
 		__syncwarp();
 		if (usable) {
 			levels[k] = lvl;
@@ -104,9 +102,7 @@ struct WarpRng {
 	// ---- cooperative refill ------------------------------------------------------------------------------------------
 	// `room` = lanes whose FIFO can take a full group.  They are served four at a time ("slot": 4 trajectories x 8
 	// candidates), each exactly once, in one run-time loop (unrolled variants blew the 32 KB instruction cache,
-	// profiles/r01_v3_*).  A trajectory's state words normally come from the shared-memory staging area that
-	// stage_ahead() filled one phase earlier with asynchronous copies; trajectories that were not staged (prediction
-	// miss, staging area full, single-step kernels) are read from global memory directly.
+	// profiles/r01_v3_*).
 	struct SlotWords {
 		uint4 a, tap;
 		uint32_t edge_next, edge_tap;
@@ -128,23 +124,12 @@ struct WarpRng {
 		w.edge_next = 0;
 		w.edge_tap = 0;
 		if (w.have) {
-			const int e = stage_of_()[w.T];
-			if (e != 0xFF) {  // staged by the previous refill's tail: already in shared memory
-				const uint4 *E = stage_() + e * RNG_STAGE_CHUNKS;
-				w.a = E[j];
-				w.tap = E[9 + j];
-				if (j == RNG_GROUP - 1) {
-					w.edge_next = E[8].x;
-					w.edge_tap = E[17].x;
-				}
-			} else {
-				const uint4 *ST = S0 + w.T * MT_CHUNKS;
-				w.a = ST[w.c];
-				w.tap = ST[mt_wrap(w.c + 99)];
-				if (j == RNG_GROUP - 1) {
-					w.edge_next = reinterpret_cast<const uint32_t *>(ST + mt_wrap(w.c + 1))[0];
-					w.edge_tap = reinterpret_cast<const uint32_t *>(ST + mt_wrap(w.c + 100))[0];
-				}
+			const uint4 *ST = S0 + w.T * MT_CHUNKS;
+			w.a = ST[w.c];
+			w.tap = ST[mt_wrap(w.c + 99)];
+			if (j == RNG_GROUP - 1) {
+				w.edge_next = reinterpret_cast<const uint32_t *>(ST + mt_wrap(w.c + 1))[0];
+				w.edge_tap = reinterpret_cast<const uint32_t *>(ST + mt_wrap(w.c + 100))[0];
 			}
 		}
 		return w;
@@ -154,7 +139,6 @@ struct WarpRng {
 	{
 		const unsigned full = 0xffffffffu;
 		const int g = lane >> 3, j = lane & 7;
-		cp_async_wait_all();  // words staged by the previous refill's tail
 		__syncwarp();
 		const int nserved = __popc(room);
 		const int slots = (nserved + 3) >> 2;
@@ -167,7 +151,7 @@ struct WarpRng {
 		int mine = 0;
 #pragma unroll 1
 		for (int s = 0; s < slots; s++) {
-			const SlotWords w = fetch(s, nserved, g, j);  // usually from the staging area: no global-memory latency here
+			const SlotWords w = fetch(s, nserved, g, j);
 			const int rdT = __shfl_sync(full, rd, w.T);
 			const int lvT = __shfl_sync(full, lvl, w.T);
 			uint32_t next = __shfl_down_sync(full, w.a.x, 1);
@@ -206,19 +190,16 @@ struct WarpRng {
 			if ((below >> 2) == s)
 				mine = __popc((okm >> ((below & 3) * RNG_GROUP)) & 0xffu);
 		}
-		__syncwarp();  // all staged words of this refill have been read
 		if (mine_served) {
 			lvl += mine;
 			chunk = mt_wrap(chunk + RNG_GROUP);
-			stage_of_()[lane] = 0xFF;  // whatever was staged for this trajectory belonged to the position just consumed
 		}
 		__syncwarp();
 	}
 
 	// Make sure every lane with `wants` holds at least `need` pairs.  Whole warp must call (convergent).
 	// Everybody with room is served, not only the needy: every slot does useful work as long as it is full.
-	// Returns whether a refill happened (warp-uniform) — the caller then calls stage_ahead() once its own global-memory
-	// loads of this round have been issued.
+	// Returns whether a refill happened (warp-uniform).
 	__device__ __forceinline__ bool ensure(bool wants, int need)
 	{
 		const unsigned full = 0xffffffffu;
@@ -228,48 +209,6 @@ struct WarpRng {
 			refilled = true;
 		}
 		return refilled;
-	}
-
-	// Stage the state words of the trajectories that will have room after their next draw (the next refill will serve
-	// exactly those) with asynchronous copies, so that their HBM latency overlaps the rest of the step phase.  The
-	// load/store unit returns data in order, so anything the warp loads from global or local memory AFTER this call
-	// waits for the copies: call it after the round's noise-memory loads.  Whole warp must call.
-	__device__ __forceinline__ void stage_ahead(bool wants, int need)
-	{
-		const unsigned full = 0xffffffffu;
-		const int g = lane >> 3, j = lane & 7;
-		const unsigned lt = (1u << lane) - 1u;
-		wants = wants && usable;
-		__syncwarp();  // everybody is done reading `order`, `stage_of` and `stage`
-		{
-			const bool will = wants && lvl - need <= CAP - RNG_GROUP;
-			const unsigned sm = __ballot_sync(full, will);
-			const int rank = __popc(sm & lt);
-			const bool staged = will && rank < RNG_STAGE_ENTRIES;
-			stage_of_()[lane] = staged ? (unsigned char)rank : (unsigned char)0xFF;
-			if (staged)
-				order_()[rank] = (unsigned char)lane;
-			__syncwarp();
-			const int nstage = min(__popc(sm), RNG_STAGE_ENTRIES);
-#pragma unroll 1
-			for (int e0 = 0; e0 < nstage; e0 += 4) {
-				const int e = e0 + g;
-				const bool have = e < nstage;
-				const int T = have ? order_()[e] : 0;
-				const int c = __shfl_sync(full, chunk, T);
-				if (have) {
-					const uint4 *ST = S0 + T * MT_CHUNKS;
-					uint4 *E = stage_() + e * RNG_STAGE_CHUNKS;
-					cp_async16(E + j, ST + mt_wrap(c + j));
-					cp_async16(E + 9 + j, ST + mt_wrap(c + 99 + j));
-					if (j == RNG_GROUP - 1) {
-						cp_async16(E + 8, ST + mt_wrap(c + 8));
-						cp_async16(E + 17, ST + mt_wrap(c + 107));
-					}
-				}
-			}
-			cp_async_commit();
-		}
 	}
 
 	// Pop this lane's next pair (caller guarantees lvl >= 1 via ensure()).
