@@ -55,7 +55,7 @@ ABI_SYMBOLS = (
 	"jsde_set_integration_parameters", "jsde_set_parameters", "jsde_pin_noise", "jsde_integrate", "jsde_integrate_jumps", "jsde_integrate_grid",
 	"jsde_get_state", "jsde_get_controller_state", "jsde_moments", "jsde_get_next_step", "jsde_get_p", "jsde_accept_step",
 	"jsde_apply_jump", "jsde_set_time", "jsde_draw_gauss_debug", "jsde_dump_noise", "jsde_measure_fp64_peak",
-	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_shared_div", "jsde_last_error", "jsde_version",
+	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_shared_div", "jsde_debug_inline_math", "jsde_last_error", "jsde_version",
 )
 
 
@@ -89,6 +89,7 @@ def _declare(lib):
 	lib.jsde_debug_log.argtypes = [ctypes.c_int, c_double_p, c_double_p, ctypes.c_int64]
 	lib.jsde_debug_pow.argtypes = [ctypes.c_int, c_double_p, ctypes.c_double, c_double_p, ctypes.c_int64]
 	lib.jsde_debug_shared_div.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, c_u8_p, ctypes.c_int64]
+	lib.jsde_debug_inline_math.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, c_u8_p, c_double_p, c_u8_p, ctypes.c_int64]
 	for name in ABI_SYMBOLS:
 		fn = getattr(lib, name)
 		if fn.restype is ctypes.c_int and name not in ("jsde_last_error", "jsde_version", "jsde_model_name"):
@@ -330,3 +331,14 @@ def device_shared_div(lib, a, b, device=0):
 	if lib.jsde_debug_shared_div(device, _dp(a), _dp(b), _dp(out), tame.ctypes.data_as(c_u8_p), a.size) != 0:
 		raise JsdeError(lib.jsde_last_error().decode())
 	return out, tame.astype(bool)
+
+
+def device_inline_math(lib, a, b, device=0):
+	"""(a/b, ok mask, sqrt(a), ok mask) through the straight-line division and square root of csrc/exact_div.cuh"""
+	a = np.ascontiguousarray(a, dtype=np.float64)
+	b = np.ascontiguousarray(b, dtype=np.float64)
+	div, root = np.empty_like(a), np.empty_like(a)
+	okd, oks = np.empty(a.size, dtype=np.uint8), np.empty(a.size, dtype=np.uint8)
+	if lib.jsde_debug_inline_math(device, _dp(a), _dp(b), _dp(div), okd.ctypes.data_as(c_u8_p), _dp(root), oks.ctypes.data_as(c_u8_p), a.size) != 0:
+		raise JsdeError(lib.jsde_last_error().decode())
+	return div, okd.astype(bool), root, oks.astype(bool)

@@ -679,6 +679,37 @@ int jsde_debug_shared_div(int device, const double *a_host, const double *b_host
 	return JSDE_OK;
 }
 
+int jsde_debug_inline_math(int device, const double *a_host, const double *b_host, double *div_host, unsigned char *div_ok_host,
+	double *sqrt_host, unsigned char *sqrt_ok_host, int64_t count)
+{
+	if (!a_host || !b_host || !div_host || !div_ok_host || !sqrt_host || !sqrt_ok_host || count < 0)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	CU(cudaSetDevice(device));
+	double *a = nullptr, *b = nullptr, *od = nullptr, *os = nullptr;
+	unsigned char *td = nullptr, *tsq = nullptr;
+	CU(cudaMalloc(&a, count * sizeof(double) + 16));
+	CU(cudaMalloc(&b, count * sizeof(double) + 16));
+	CU(cudaMalloc(&od, count * sizeof(double) + 16));
+	CU(cudaMalloc(&os, count * sizeof(double) + 16));
+	CU(cudaMalloc(&td, count + 16));
+	CU(cudaMalloc(&tsq, count + 16));
+	cudaError_t err = cudaMemcpy(a, a_host, count * sizeof(double), cudaMemcpyHostToDevice);
+	if (err == cudaSuccess) err = cudaMemcpy(b, b_host, count * sizeof(double), cudaMemcpyHostToDevice);
+	if (err == cudaSuccess) {
+		k_debug_inline_math<<<grid_for(count, 256), 256>>>(a, b, od, td, os, tsq, count);
+		err = cudaGetLastError();
+	}
+	if (err == cudaSuccess) err = cudaMemcpy(div_host, od, count * sizeof(double), cudaMemcpyDeviceToHost);
+	if (err == cudaSuccess) err = cudaMemcpy(sqrt_host, os, count * sizeof(double), cudaMemcpyDeviceToHost);
+	if (err == cudaSuccess) err = cudaMemcpy(div_ok_host, td, count, cudaMemcpyDeviceToHost);
+	if (err == cudaSuccess) err = cudaMemcpy(sqrt_ok_host, tsq, count, cudaMemcpyDeviceToHost);
+	cudaFree(a); cudaFree(b); cudaFree(od); cudaFree(os); cudaFree(td); cudaFree(tsq);
+	if (err != cudaSuccess)
+		return fail(JSDE_E_CUDA, cudaGetErrorString(err));
+	return JSDE_OK;
+}
+
+
 int jsde_debug_log(int device, const double *x_host, double *out_host, int64_t count) { return debug_unary(device, x_host, out_host, count, 0, 0.0); }
 int jsde_debug_pow(int device, const double *x_host, double y, double *out_host, int64_t count) { return debug_unary(device, x_host, out_host, count, 1, y); }
 

@@ -390,6 +390,7 @@ int jsde_dump_noise(jsde_t *, int64_t, double *, int, int *) { return unsupporte
 int jsde_debug_log(int, const double *, double *, int64_t) { return unsupported("debug_log"); }
 int jsde_debug_pow(int, const double *, double, double *, int64_t) { return unsupported("debug_pow"); }
 int jsde_debug_shared_div(int, const double *, const double *, double *, unsigned char *, int64_t) { return unsupported("debug_shared_div"); }
+int jsde_debug_inline_math(int, const double *, const double *, double *, unsigned char *, double *, unsigned char *, int64_t) { return unsupported("debug_inline_math"); }
 
 int jsde_measure_fp64_peak(int device, double *tflops)
 {

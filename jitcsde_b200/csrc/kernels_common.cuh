@@ -119,6 +119,21 @@ __global__ void k_debug_shared_div(const double *a, const double *b, double *out
 	}
 }
 
+// out_div[i] = a[i]/b[i] and out_sqrt[i] = sqrt(a[i]) through the straight-line restatements of exact_div.cuh, with their
+// validity flags
+__global__ void k_debug_inline_math(const double *a, const double *b, double *out_div, unsigned char *ok_div, double *out_sqrt,
+	unsigned char *ok_sqrt, int64_t count)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) {
+		bool okd = true, oks = true;
+		out_div[i] = inline_div(a[i], b[i], okd);
+		out_sqrt[i] = inline_sqrt(a[i], oks);
+		ok_div[i] = okd ? 1 : 0;
+		ok_sqrt[i] = oks ? 1 : 0;
+	}
+}
+
 __global__ void k_debug_pow(const double *x, double yexp, double *out, int64_t count)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

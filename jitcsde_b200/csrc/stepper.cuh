@@ -169,11 +169,21 @@ struct Lane {
 				if (i == which)
 					lg[i] = v;
 		}
+		// f = scale*sqrt(-2*log(r2)/r2) for all components in straight-line code (exact_div.cuh)
+		double f[N];
+		bool tame = true;
+#pragma unroll
+		for (int i = 0; i < N; i++)
+			f[i] = scale * inline_sqrt(inline_div(__dmul_rn(-2.0, lg[i]), r2[i], tame), tame);
+		if (!tame) {  // cold: operands near the ends of the exponent range
+#pragma unroll
+			for (int i = 0; i < N; i++)
+				f[i] = scale * sqrt(__ddiv_rn(__dmul_rn(-2.0, lg[i]), r2[i]));
+		}
 #pragma unroll
 		for (int i = 0; i < N; i++) {
-			const double f = scale * sqrt(__ddiv_rn(__dmul_rn(-2.0, lg[i]), r2[i]));
-			gW[i] *= f;
-			gZ[i] *= f;
+			gW[i] *= f[i];
+			gZ[i] *= f[i];
 		}
 	}
 
@@ -407,14 +417,29 @@ struct Lane {
 	// get_p (template:502-526): a 0/0 component is skipped, a NaN never wins the comparison
 	__device__ __forceinline__ double error_ratio(double atol, double rtol) const
 	{
+		// the N quotients in straight-line code (exact_div.cuh); a zero error needs no division: 0/tol is +0 or — for a
+		// NaN tolerance — a NaN, and neither can win the comparison below
+		double tol[N], x[N];
+		bool tame = true;
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			tol[i] = atol + rtol * fabs(ny[i]);
+			bool mine = true;
+			const double q = inline_div(er[i], tol[i], mine);
+			x[i] = er[i] == 0.0 ? 0.0 : q;
+			tame = tame && (mine || er[i] == 0.0);
+		}
+		if (!tame) {  // cold
+#pragma unroll
+			for (int i = 0; i < N; i++)
+				x[i] = er[i] / tol[i];
+		}
 		double worst = 0.0;
 #pragma unroll
 		for (int i = 0; i < N; i++) {
-			const double tol = atol + rtol * fabs(ny[i]);
-			if (er[i] != 0.0 || tol != 0.0) {
-				const double x = er[i] / tol;
-				if (x > worst)
-					worst = x;
+			if (er[i] != 0.0 || tol[i] != 0.0) {
+				if (x[i] > worst)
+					worst = x[i];
 			}
 		}
 		return worst;

@@ -91,6 +91,53 @@ def test_shared_divisor_division_is_exact():
 	assert list(tame) == [False, False, False, False, True] and got[4] == 0.0
 
 
+def test_inline_division_and_sqrt_are_exact():
+	"""exact_div.cuh: the straight-line restatements of nvcc's FP64 division and square root give the operators' bits
+	wherever they vouch for the result, vouch for everything the integrator feeds them, and decline at the ends of
+	the exponent range."""
+	lib = _abi.load_library(models.lorenz_additive)
+	rng = np.random.default_rng(12)
+	N = 1 << 24
+	def mant(n):
+		return 1.0 + rng.integers(0, 1 << 52, n, dtype=np.uint64).astype(np.float64) / 2.0 ** 52
+	cases = []
+	for _ in range(4):
+		cases.append((mant(N) * 2.0 ** rng.integers(-900, 900, N) * rng.choice([-1.0, 1.0], N), mant(N) * 2.0 ** rng.integers(-900, 900, N) * rng.choice([-1.0, 1.0], N)))
+	# what the Gaussian factor really divides: -2 log(r2) / r2 for radii in (0, 1), and error/tolerance ratios
+	r2 = rng.random(N)
+	cases.append((-2.0 * np.log(r2), r2))
+	r2 = 2.0 ** -rng.uniform(0, 104, N)
+	cases.append((-2.0 * np.log(r2), r2))
+	cases.append((np.abs(rng.standard_normal(N)) * 10.0 ** rng.uniform(-30, 3, N), 1e-10 + 1e-5 * np.abs(rng.standard_normal(N)) * 10.0 ** rng.uniform(-3, 3, N)))
+	# hard patterns: divisor mantissa all ones, quotients at rounding boundaries, perfect squares and their neighbours
+	cases.append((mant(N), np.nextafter(2.0, 0.0) * 2.0 ** rng.integers(-50, 50, N)))
+	q = mant(N); b2 = mant(N)
+	cases.append((q * b2, b2))
+	cases.append((np.nextafter(q * b2, np.inf), b2))
+	s = mant(N) * 2.0 ** rng.integers(-200, 200, N)
+	cases.append((s * s, mant(N)))
+	cases.append((np.nextafter(s * s, 0.0), mant(N)))
+	vouched_div = vouched_sqrt = 0
+	for i, (a, b) in enumerate(cases):
+		div, okd, root, oks = _abi.device_inline_math(lib, a, b)
+		with np.errstate(all="ignore"):
+			assert_bits_equal(div[okd], (a / b)[okd], "inline quotient")
+			assert_bits_equal(root[oks], np.sqrt(a)[oks], "inline square root")
+		if 4 <= i <= 6:  # the integrator's own operand ranges: no fallbacks
+			assert okd.all()
+		if 4 <= i <= 5 or i >= 10:
+			assert oks.all()
+		vouched_div += okd.sum(); vouched_sqrt += oks.sum()
+	assert vouched_div > 8 * N and vouched_sqrt > 5 * N
+	# specials are declined, never guessed
+	a = np.array([0.0, 1.0, np.inf, np.nan, 1.0, 1.0, 1e-320, -1.0, 1e308])
+	b = np.array([3.0, 0.0, 2.0, 2.0, np.inf, np.nan, 1.0, 1.0, 1e-308])
+	div, okd, root, oks = _abi.device_inline_math(lib, a, b)
+	assert list(okd) == [False, False, False, False, False, False, False, True, False] and div[7] == -1.0
+	assert not oks[[0, 2, 3, 6, 7]].any() and oks[[1, 4, 5, 8]].all()  # zero, inf, NaN, subnormal, negative are declined
+	assert_bits_equal(root[oks], np.sqrt(a[oks]), "inline square root")
+
+
 # ---- Gaussian stream --------------------------------------------------------------------------------------------------
 def test_gauss_stream_bit_exact_many_seeds():
 	"""rk_gauss pairs per trajectory == oracle, across several regenerations of the 624-word block."""
