@@ -37,6 +37,11 @@ sys.path.insert(0, ROOT)
 FLOP_PER_ACCEPTED = 235.0   # SRA-Lorenz, one fresh draw per attempt, 1.04 attempts per accepted step
 BYTES_PER_ATTEMPT = 235.0   # generator state + one noise item streamed through HBM
 FP64_NOMINAL_TFLOPS = 37.2  # 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz
+# DRAM traffic of the integrate kernel per attempted step, from one `ncu --set full` capture of the steady state
+# (profiles/r01_duo_final_ncu_summary.txt: dram__bytes_read.sum 23.66 GB + dram__bytes_write.sum 16.46 GB for
+# 2.7335e8 attempts at B=2^18).  A full-size launch (17 s) cannot be replayed under ncu within the GPU budget, so
+# `roofline.traffic` is this per-attempt figure times the attempts of one launch.
+NCU_DRAM_BYTES_PER_ATTEMPT = (23.661648e9 + 16.464983e9) / 273349641
 
 
 def measured_peaks():
@@ -274,7 +279,11 @@ def run_gpu_arm(args):
 			"gpu_launches": launches, "clocks": clocks,
 			"accepted_per_step": accepted // args.steps, "rejected_per_step": rejected // args.steps, "failed_trajectories": failed,
 			"roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp64_peak,
-				"traffic": None, "per_gpu": True, "flop_per_accepted_step": FLOP_PER_ACCEPTED,
+				"traffic": NCU_DRAM_BYTES_PER_ATTEMPT * attempts / args.steps / world,
+				"traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per attempt (B=2^18 steady-state capture, "
+					"profiles/r01_duo_final_ncu_summary.txt) x attempts of one launch; algorithmic bytes per launch = "
+					f"{BYTES_PER_ATTEMPT:g} B x attempts",
+				"per_gpu": True, "flop_per_accepted_step": FLOP_PER_ACCEPTED,
 				"peak_source": "dependent-chain DFMA kernel measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
 				"hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0),
 					"bytes_per_attempt": BYTES_PER_ATTEMPT, "peak_source": peaks_src}},
