@@ -27,6 +27,12 @@
 // disjoint because `added` is bounded by the room computed from the *published* (older, smaller) popped count.
 // Both loops leave on the same published mask == 0.  The producer owns the persistence of queued pairs between
 // launches (same spill format as WarpRng, which the single-step kernels use).
+//
+// Trajectory recycling: the grid is at most one wave of blocks; a lane whose trajectory is done takes the next one
+// from a pool (atomic counter) instead of idling until its warp's and block's slowest trajectory finishes (7 % of the
+// headline run).  The consumer announces the change through `swap[lane]` together with the final popped count of the
+// old trajectory; the producer then spills the old trajectory's queued pairs and stream position, loads the new
+// one's, and refills — the lane sits out that one round.
 #pragma once
 
 #include "warp_rng.cuh"
@@ -74,14 +80,16 @@ template <int N>
 struct PairLayout {
 	static constexpr int CAP = WarpRng<N>::CAP;
 	static constexpr int FIFO_DOUBLES = 3 * CAP * RNG_STRIDE;
-	// FIFOs x1, x2, r2 [CAP][RNG_STRIDE] | popped[2][32] u32 | mask[2] u32 | order[32] u8 | stage[3][4][18] uint4
+	// FIFOs x1, x2, r2 [CAP][RNG_STRIDE] | popped[2][32] u32 | mask[2] u32 | order[32] u8 | swap[2][32] i32 | stage[3][4][18] uint4
 	static constexpr int STAGE_DEPTH = JSDE_DUO_STAGE_AHEAD + 1;  // slots whose generator words are in flight (cp.async) or being processed
-	static constexpr int STAGE_OFFSET = (FIFO_DOUBLES + 32 + 1 + 4 + 1) & ~1;  // 16-byte aligned
+	static constexpr int STAGE_OFFSET = (FIFO_DOUBLES + 32 + 1 + 4 + 32 + 1) & ~1;  // 16-byte aligned
 	static constexpr int DOUBLES = STAGE_OFFSET + STAGE_DEPTH * 4 * RNG_STAGE_CHUNKS * 2;
 	static __device__ __forceinline__ uint4 *stage(double *base, int buf, int g) { return reinterpret_cast<uint4 *>(base + STAGE_OFFSET) + (buf * 4 + g) * RNG_STAGE_CHUNKS; }
 	static __device__ __forceinline__ unsigned *popped(double *base, int parity) { return reinterpret_cast<unsigned *>(base + FIFO_DOUBLES) + 32 * parity; }
 	static __device__ __forceinline__ unsigned *mask(double *base, int parity) { return reinterpret_cast<unsigned *>(base + FIFO_DOUBLES + 32) + parity; }
 	static __device__ __forceinline__ unsigned char *order(double *base) { return reinterpret_cast<unsigned char *>(base + FIFO_DOUBLES + 33); }
+	// swap[2][32] i32: trajectory a lane switches to in this round (-1: none)
+	static __device__ __forceinline__ int *swap(double *base, int parity) { return reinterpret_cast<int *>(base + FIFO_DOUBLES + 37) + 32 * parity; }
 };
 
 // ---- consumer side: what Lane<> needs from its pair source ---------------------------------------------------------
@@ -113,13 +121,19 @@ struct PairConsumer {
 		popped++;
 	}
 
-	// publish this lane's progress, meet the producer; returns the lanes that still have work (warp-uniform)
-	__device__ __forceinline__ unsigned rendezvous(bool active)
+	// publish this lane's progress (and the trajectory it switches to, if any: `next_trajectory` >= 0), meet the
+	// producer; returns the lanes that still have work (warp-uniform)
+	__device__ __forceinline__ unsigned rendezvous(bool active, int next_trajectory)
 	{
 		const unsigned act = __ballot_sync(0xffffffffu, active);
-		L::popped(base, parity)[lane] = popped;
+		L::popped(base, parity)[lane] = popped;  // on a switch: the old trajectory's final count
+		L::swap(base, parity)[lane] = next_trajectory;
 		if (lane == 0)
 			*L::mask(base, parity) = act;
+		if (next_trajectory >= 0) {  // the new trajectory's queue starts at slot 0
+			rd = 0;
+			popped = 0;
+		}
 		parity ^= 1;
 		__syncwarp();
 		pair_barrier(pair);
@@ -133,14 +147,14 @@ struct PairProducer {
 	using L = PairLayout<N>;
 	static constexpr int CAP = L::CAP;
 	double *base;
-	uint4 *S0;  // generator record of the pair's lane-0 trajectory
+	uint4 *mt;  // generator records [B][156]
 	int pair, lane;
-	int wr, lvl, chunk;  // this lane's trajectory: ring write slot, (lower bound of the) fill level, next chunk
+	int traj;            // this lane's trajectory (-1: none yet)
+	int wr, lvl, chunk;  // its ring write slot, (lower bound of the) fill level, next chunk
 	unsigned pushed;
-	bool usable;
 
-	__device__ __forceinline__ PairProducer(double *pair_smem, int pair_index, uint4 *mt, int64_t k_lane0, bool live)
-		: base(pair_smem), S0(mt + k_lane0 * MT_CHUNKS), pair(pair_index), lane(threadIdx.x & 31), wr(0), lvl(0), chunk(0), pushed(0), usable(live) {}
+	__device__ __forceinline__ PairProducer(double *pair_smem, int pair_index, uint4 *records)
+		: base(pair_smem), mt(records), pair(pair_index), lane(threadIdx.x & 31), traj(-1), wr(0), lvl(0), chunk(0), pushed(0) {}
 
 	__device__ __forceinline__ double *fx1_() const { return base; }
 	__device__ __forceinline__ double *fx2_() const { return base + CAP * RNG_STRIDE; }
@@ -149,7 +163,7 @@ struct PairProducer {
 	// queued pairs of the previous launch go to ring slots 0..lvl-1 (the consumer starts reading at slot 0)
 	__device__ __forceinline__ void load(const double *spill, const int *levels, const int *chunks, int64_t B, int64_t k)
 	{
-		if (usable) {
+		{
 			lvl = levels[k];
 			chunk = chunks[k];
 			for (int i = 0; i < lvl; i++) {
@@ -164,7 +178,7 @@ struct PairProducer {
 
 	__device__ __forceinline__ void store(double *spill, int *levels, int *chunks, int64_t B, int64_t k) const
 	{
-		if (usable) {
+		{
 			levels[k] = lvl;
 			chunks[k] = chunk;
 			int s = wr - lvl;
@@ -189,8 +203,9 @@ struct PairProducer {
 		const bool have = 4 * s + g < nserved;
 		const int T = L::order(base)[rank] & 31;  // absent ranks: a stale but valid lane number, only ever used for shuffles
 		const int c = __shfl_sync(0xffffffffu, chunk, T);
+		const int kT = __shfl_sync(0xffffffffu, traj, T);
 		if (have) {
-			const uint4 *ST = S0 + T * MT_CHUNKS;
+			const uint4 *ST = mt + (int64_t)kT * MT_CHUNKS;
 			uint4 *E = L::stage(base, s % L::STAGE_DEPTH, g);
 			cp_async16(E + j, ST + mt_wrap(c + j));
 			cp_async16(E + 9 + j, ST + mt_wrap(c + 99 + j));
@@ -229,6 +244,7 @@ struct PairProducer {
 			const int T = L::order(base)[rank] & 31;
 			const int c = mt_wrap(__shfl_sync(full, chunk, T) + j);
 			const int wrT = __shfl_sync(full, wr, T);
+			const int kT = __shfl_sync(full, traj, T);
 			bool ok = false;
 			double x1 = 0.0, x2 = 0.0, r2 = 0.0;
 			if (have) {
@@ -240,7 +256,7 @@ struct PairProducer {
 				r.y = mt_twist(a.y, a.z, tap.z);
 				r.z = mt_twist(a.z, a.w, tap.w);
 				r.w = mt_twist(a.w, next, tap_hi);
-				S0[T * MT_CHUNKS + c] = r;
+				mt[(int64_t)kT * MT_CHUNKS + c] = r;
 				uint4 v;
 				v.x = mt_temper(a.x);
 				v.y = mt_temper(a.y);
@@ -272,7 +288,7 @@ struct PairProducer {
 	}
 
 	// the producer warp's whole life
-	__device__ __forceinline__ void run()
+	__device__ __forceinline__ void run(double *spill, int *levels, int *chunks, int64_t B)
 	{
 		const unsigned full = 0xffffffffu;
 		int parity = 0;
@@ -280,13 +296,23 @@ struct PairProducer {
 			pair_barrier(pair);
 			const unsigned act = *L::mask(base, parity);
 			lvl = (int)(pushed - L::popped(base, parity)[lane]);
+			const int next = L::swap(base, parity)[lane];
 			parity ^= 1;
+			if (next >= 0) {  // the consumer lane has moved on to another trajectory
+				if (traj >= 0)
+					store(spill, levels, chunks, B, traj);
+				traj = next;
+				load(spill, levels, chunks, B, traj);
+			}
+			__syncwarp();
 			if (!act)
 				break;
-			const bool wants = usable && ((act >> lane) & 1u);
+			const bool wants = traj >= 0 && ((act >> lane) & 1u);
 			while (__ballot_sync(full, wants && lvl < 2 * N))
 				refill(__ballot_sync(full, wants && lvl <= CAP - RNG_GROUP));
 		}
+		if (traj >= 0)
+			store(spill, levels, chunks, B, traj);  // queued pairs and stream position survive until the next launch
 	}
 };
 

@@ -39,6 +39,7 @@ struct CallTotals {
 	unsigned long long accepted, rejected, fresh_draws, jumps;
 	long long n_min_step, n_overflow;
 	int max_depth;
+	unsigned long long pool_taken;  // trajectories handed out beyond the grid's first wave (k_integrate recycles lanes)
 };
 
 struct EnsembleView {

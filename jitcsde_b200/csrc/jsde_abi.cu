@@ -46,6 +46,8 @@ struct jsde_handle {
 	int device = 0;
 	int64_t B = 0;
 	int D = 0;
+	int resident_blocks = 0;  // blocks of k_integrate that fit on the device at once
+	bool recycle = false;     // lanes take further trajectories from a pool (grid = one wave): see kernels.cuh
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	EnsembleView v{};
@@ -152,7 +154,7 @@ int jsde_model_info(int *n, int *additive, int *n_params, int *has_jump)
 
 int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 {
-	if (!out || B <= 0 || noise_capacity < 0)
+	if (!out || B <= 0 || B >= 0x7fffffff || noise_capacity < 0)
 		return fail(JSDE_E_ARG, "Wrong input.");
 	int count = 0;
 	cudaError_t err = cudaGetDeviceCount(&count);
@@ -211,12 +213,26 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	// the generator FIFOs + staging area exceed the 48 KB default for dynamic shared memory
 	const int smem = (int)rng_smem_bytes<Model>();
 	const int duo_smem = (int)duo_smem_bytes<Model>();
-	if ((err = cudaFuncSetAttribute(k_integrate<Model, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, duo_smem)) != cudaSuccess ||
-		(err = cudaFuncSetAttribute(k_integrate<Model, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, duo_smem)) != cudaSuccess ||
+	if ((err = cudaFuncSetAttribute(k_integrate<Model, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, duo_smem)) != cudaSuccess ||
+		(err = cudaFuncSetAttribute(k_integrate<Model, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, duo_smem)) != cudaSuccess ||
+		(err = cudaFuncSetAttribute(k_integrate<Model, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, duo_smem)) != cudaSuccess ||
+		(err = cudaFuncSetAttribute(k_integrate<Model, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, duo_smem)) != cudaSuccess ||
 		(err = cudaFuncSetAttribute(k_get_next_step<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
 		(err = cudaFuncSetAttribute(k_pin_noise<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
 		(err = cudaFuncSetAttribute(k_draw_gauss<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
 		return bail(fail(JSDE_E_CUDA, cudaGetErrorString(err)));
+	{
+		int per_sm = 0;
+		cudaDeviceProp prop;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_integrate<Model, false, true>, DUO_BLOCK, duo_smem) == cudaSuccess &&
+			cudaGetDeviceProperties(&prop, device) == cudaSuccess && per_sm > 0)
+			h->resident_blocks = per_sm * prop.multiProcessorCount;
+		h->recycle = !Model::ADDITIVE;
+		if (const char *env = getenv("JSDE_RECYCLE"))
+			h->recycle = atoi(env) != 0;
+		if (const char *env = getenv("JSDE_RESIDENT_BLOCKS"))  // test knob: a tiny grid makes small ensembles recycle lanes
+			if (atoi(env) > 0) h->resident_blocks = atoi(env);
+	}
 	*out = h;
 	return JSDE_OK;
 }
@@ -338,11 +354,21 @@ static int integrate_common(jsde_t *h, double target_time, int use_tape, jsde_st
 		return fail(JSDE_E_ARG, "Wrong input. (target time is NaN)");
 	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
 	CU(cudaEventRecord(h->ev0, h->stream));
-	if (grid_times_dev)
-		k_integrate<Model, true><<<grid_for(h->B, 32 * DUO_PAIRS), DUO_BLOCK, duo_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
+	const unsigned all_blocks = grid_for(h->B, 32 * DUO_PAIRS);
+	if (h->recycle && h->resident_blocks > 0 && all_blocks > (unsigned)h->resident_blocks) {
+		// one wave of blocks: lanes take further trajectories from a pool as theirs finish (kernels.cuh)
+		const unsigned grid = (unsigned)h->resident_blocks;
+		if (grid_times_dev)
+			k_integrate<Model, true, true><<<grid, DUO_BLOCK, duo_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
+				grid_times_dev, grid_count, grid_out_dev);
+		else
+			k_integrate<Model, false, true><<<grid, DUO_BLOCK, duo_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
+				nullptr, 0, nullptr);
+	} else if (grid_times_dev)
+		k_integrate<Model, true, false><<<all_blocks, DUO_BLOCK, duo_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
 			grid_times_dev, grid_count, grid_out_dev);
 	else
-		k_integrate<Model, false><<<grid_for(h->B, 32 * DUO_PAIRS), DUO_BLOCK, duo_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
+		k_integrate<Model, false, false><<<all_blocks, DUO_BLOCK, duo_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
 			nullptr, 0, nullptr);
 	CU(cudaGetLastError());
 	return finish_call(h, stats_host, 1);

@@ -79,7 +79,11 @@ __device__ __forceinline__ WarpRng<Model::N> make_rng(const EnsembleView &e, int
 template <class Model>
 constexpr size_t duo_smem_bytes() { return ((size_t)DUO_PAIRS * PairLayout<Model::N>::DOUBLES + MATH_TAB_DOUBLES) * sizeof(double); }
 
-template <class Model, bool GRID>
+// RECYCLE: the grid is one wave of blocks and a lane whose trajectory is done takes the next one from a pool.  Pays when
+// the trajectories' step counts differ a lot (multiplicative noise: +26 % on SRI-Lorenz to t = 10); costs ~2 % cycles
+// and, under the power cap, ~2 % clock when they do not (additive Lorenz to t = 100: step counts within 1 %), so the
+// host enables it for non-additive models (JSDE_RECYCLE=0/1 overrides).
+template <class Model, bool GRID, bool RECYCLE>
 __global__ void __launch_bounds__(DUO_BLOCK, JSDE_DUO_MIN_BLOCKS) k_integrate(EnsembleView e, Controller c, double target, int use_tape,
 	const double *__restrict__ grid_times_, int grid_count, double *__restrict__ grid_out)
 {
@@ -88,17 +92,12 @@ __global__ void __launch_bounds__(DUO_BLOCK, JSDE_DUO_MIN_BLOCKS) k_integrate(En
 	stage_math_tables(jsde_smem);
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int pair = warp & (DUO_PAIRS - 1);
-	const int64_t k = ((int64_t)blockIdx.x * DUO_PAIRS + pair) * 32 + lane;
-	const bool live = k < e.B;
-	const int64_t kk = live ? k : 0;
 	double *pair_smem = jsde_smem + MATH_TAB_DOUBLES + pair * PairLayout<N>::DOUBLES;
 
 	if (warp >= DUO_PAIRS) {  // ---- producer warpgroup ----
 		setmaxnreg_dec<JSDE_DUO_PRODUCER_REGS>();
-		PairProducer<N> P(pair_smem, pair, e.mt, k - lane, live);
-		P.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
-		P.run();
-		P.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+		PairProducer<N> P(pair_smem, pair, e.mt);
+		P.run(e.rng_spill, e.rng_level, e.mt_chunk, e.B);
 		return;
 	}
 
@@ -108,50 +107,99 @@ __global__ void __launch_bounds__(DUO_BLOCK, JSDE_DUO_MIN_BLOCKS) k_integrate(En
 	// Sampling-grid mode (grid_times != nullptr): the lane integrates to grid_times[0], records its state in
 	// grid_out[0][·][k], goes on to grid_times[1], … — exactly the sequence of integrate() calls of
 	// examples/noisy_lorenz.py:95-96 (truncated last step + Brownian bridge at every sample time), in one launch.
-	int grid_index = 0;
-	if (grid_times)
-		target = grid_times[0];
 	PairConsumer<N> rng(pair_smem, jsde_smem, pair);
-	Lane<Model, PairConsumer<N>> L(e, kk, rng);
+	Lane<Model, PairConsumer<N>> L(e, 0, rng);
+	// This lane starts with the trajectory of its global index and (RECYCLE) takes the next one from the pool whenever
+	// its trajectory is done (duo.cuh).  Results do not depend on which lane integrates a trajectory.
+	int k = -1;  // B < 2^31 (jsde_create)
+	int upcoming = (int)min((int64_t)0x7fffffff, ((int64_t)blockIdx.x * DUO_PAIRS + pair) * 32 + lane);
 	unsigned acc = 0, rej = 0, jumps = 0;  // per call and trajectory: far below 2^32 (the noise memory would overflow first)
+	int grid_index = 0;
+	double cur_target = target;  // differs from `target` only in sampling-grid mode
 	double next_jump = 0.0;
 	bool jump_set = false;
 	long long tape_pos = 0;
-	bool active = false;
-	if (live) {
-		L.load();
-		if (L.status == TRAJ_MIN_STEP)
-			L.status = TRAJ_OK;  // the reference raises once per call and lets the caller carry on (:569-579)
-		L.cursor = 0;
-		if (Model::HAS_JUMP && use_tape) {
-			next_jump = e.next_jump[k];
-			jump_set = e.jump_set[k] != 0;
-			tape_pos = e.tape_pos[k];
-		}
-		active = L.status == TRAJ_OK;
-	}
+	bool active = false, sit_out = false;
 	bool need_target = true, to_jump = false;
 	double tgt = target;
 	bool primed = false;  // round 0 is empty: the producer fills the FIFOs for the first time
-	while (rng.rendezvous(active)) {
+	// Two nested loops: the inner one is the hot round loop; the outer one (cold) hands finished trajectories back and
+	// takes new ones, so that its register needs do not shape the allocation of the hot loop.
+	bool finished = false;
+	while (!finished) {
+		int next_trajectory = -1;
+		if (!active && upcoming >= 0) {
+			if (k >= 0) {  // hand back the finished trajectory
+				L.store();
+				if (Model::HAS_JUMP && use_tape) {
+					e.next_jump[k] = next_jump;
+					e.jump_set[k] = jump_set ? 1 : 0;
+					e.tape_pos[k] = tape_pos;
+				}
+				e.accepted[k] += acc;
+				e.rejected[k] += rej;
+				CallTotals *tot = e.totals;  // once per trajectory: cheaper than carrying running sums in registers
+				if (acc) atomicAdd(&tot->accepted, (unsigned long long)acc);
+				if (rej) atomicAdd(&tot->rejected, (unsigned long long)rej);
+				if (L.fresh) atomicAdd(&tot->fresh_draws, (unsigned long long)L.fresh);
+				if (jumps) atomicAdd(&tot->jumps, (unsigned long long)jumps);
+				if (L.status == TRAJ_MIN_STEP) atomicAdd((unsigned long long *)&tot->n_min_step, 1ull);
+				if (L.status == TRAJ_NOISE_OVERFLOW) atomicAdd((unsigned long long *)&tot->n_overflow, 1ull);
+				if (L.max_depth) atomicMax(&tot->max_depth, L.max_depth);
+				upcoming = RECYCLE ? (int)min(0x7fffffffull, (unsigned long long)gridDim.x * (DUO_PAIRS * 32) + atomicAdd(&tot->pool_taken, 1ull)) : -1;
+				k = -1;
+			}
+			if (upcoming >= 0 && upcoming < e.B) {  // take the next trajectory; this lane sits out the round in which its queue is rebuilt
+				k = upcoming;
+				next_trajectory = k;
+				L.rebind(k);
+				L.load();
+				if (L.status == TRAJ_MIN_STEP)
+					L.status = TRAJ_OK;  // the reference raises once per call and lets the caller carry on (:569-579)
+				L.cursor = 0;
+				L.fresh = 0;
+				L.max_depth = 0;
+				acc = rej = jumps = 0;
+				if (Model::HAS_JUMP && use_tape) {
+					next_jump = e.next_jump[k];
+					jump_set = e.jump_set[k] != 0;
+					tape_pos = e.tape_pos[k];
+				}
+				grid_index = 0;
+				cur_target = grid_times ? grid_times[0] : target;
+				need_target = true;
+				to_jump = false;
+				active = L.status == TRAJ_OK;  // a trajectory that cannot run is handed back in the next round
+				sit_out = true;
+			} else
+				upcoming = -1;  // pool exhausted
+		}
+		while (true) {
+		if (!rng.rendezvous(active, next_trajectory)) {
+			finished = true;
+			break;
+		}
+		next_trajectory = -1;
+		const bool resting = sit_out;  // the producer is rebuilding this lane's queue
+		sit_out = false;
 		if (!primed) {
 			primed = true;
 			continue;
 		}
 		bool attempt = false, last = false;
 		double actual_dt = 0.0;
-		if (active) {
+		if (active && !resting) {
 			attempt = true;
 			if (need_target) {
-				tgt = target;
+				tgt = GRID ? cur_target : target;
 				to_jump = false;
 				if (Model::HAS_JUMP && use_tape) {
 					if (!jump_set) {  // next_jump property (:682-687): t + IJI(t, y)
-						const double wait = tape_pos < e.tape_len ? e.taus[k * e.tape_len + tape_pos] : __longlong_as_double(0x7ff0000000000000LL);
+						const double wait = tape_pos < e.tape_len ? e.taus[(int64_t)k * e.tape_len + tape_pos] : __longlong_as_double(0x7ff0000000000000LL);
 						next_jump = L.t + wait;
 						jump_set = true;
 					}
-					if (next_jump < target) {
+					if (next_jump < (GRID ? cur_target : target)) {
 						tgt = next_jump;
 						to_jump = true;
 					}
@@ -166,14 +214,14 @@ __global__ void __launch_bounds__(DUO_BLOCK, JSDE_DUO_MIN_BLOCKS) k_integrate(En
 							for (int i = 0; i < N; i++)
 								grid_out[((int64_t)grid_index * N + i) * e.B + k] = L.y[i];
 							if (++grid_index < grid_count) {
-								target = grid_times[grid_index];
+								cur_target = grid_times[grid_index];
 								need_target = true;
 								active = true;
 							}
 						}
 					} else {
 						double change[N];
-						Model::jump(L.t, L.y, e.xis[k * e.tape_len + tape_pos], L.par, change);
+						Model::jump(L.t, L.y, e.xis[(int64_t)k * e.tape_len + tape_pos], L.par, change);
 #pragma unroll
 						for (int i = 0; i < N; i++)
 							L.y[i] += change[i];
@@ -207,14 +255,14 @@ __global__ void __launch_bounds__(DUO_BLOCK, JSDE_DUO_MIN_BLOCKS) k_integrate(En
 								for (int i = 0; i < N; i++)
 									grid_out[((int64_t)grid_index * N + i) * e.B + k] = L.y[i];
 								if (++grid_index < grid_count) {
-									target = grid_times[grid_index];
+									cur_target = grid_times[grid_index];
 									need_target = true;
 									active = true;
 								}
 							}
 						} else {
 							double change[N];  // apply_jump(amp(time, state)) (:696-698)
-							Model::jump(L.t, L.y, e.xis[k * e.tape_len + tape_pos], L.par, change);
+							Model::jump(L.t, L.y, e.xis[(int64_t)k * e.tape_len + tape_pos], L.par, change);
 #pragma unroll
 							for (int i = 0; i < N; i++)
 								L.y[i] += change[i];
@@ -233,21 +281,12 @@ __global__ void __launch_bounds__(DUO_BLOCK, JSDE_DUO_MIN_BLOCKS) k_integrate(En
 				}
 			}
 		}
-	}
-	int failed_min = 0, failed_ovf = 0;
-	if (live) {
-		L.store();
-		if (Model::HAS_JUMP && use_tape) {
-			e.next_jump[k] = next_jump;
-			e.jump_set[k] = jump_set ? 1 : 0;
-			e.tape_pos[k] = tape_pos;
+		if (__any_sync(0xffffffffu, !active && upcoming >= 0))
+			break;  // somebody has a trajectory to hand back (and perhaps one to take)
 		}
-		e.accepted[k] += acc;
-		e.rejected[k] += rej;
-		failed_min = L.status == TRAJ_MIN_STEP;
-		failed_ovf = L.status == TRAJ_NOISE_OVERFLOW;
 	}
-	add_totals(e.totals, acc, rej, live ? L.fresh : 0, jumps, failed_min, failed_ovf, live ? L.max_depth : 0);
+	// every lane has handed back its last trajectory before the loop can end: a lane with a trajectory is active or about
+	// to hand it back, and keeps `upcoming >= 0` until the pool is exhausted
 }
 
 // ---- single-step surface (reference core methods, one launch each) ---------------------------------------------

@@ -25,11 +25,11 @@ struct Lane {
 	static constexpr int NP = Model::NPAR;
 
 	const EnsembleView &e;
-	const int64_t k;
+	int64_t k;
 	static constexpr int IT = noise_item_doubles(N);  // one noise item: {h, DW[N], DZ[N]} padded to 16-byte pairs
 
 	Rng &rng;  // source of accepted polar pairs: pop(x1, x2, r2) and the shared-memory log table
-	double *const q0;  // item 0 of this trajectory's noise memory; item d is at q0 + d*B*IT
+	double *q0;  // slot 0 of this trajectory's noise memory; slot s is at q0 + s*B*IT
 
 	double y[N], t, dt;
 	double ny[N], er[N], nt;  // last proposal
@@ -40,6 +40,13 @@ struct Lane {
 
 	__device__ __forceinline__ Lane(const EnsembleView &view, int64_t index, Rng &source)
 		: e(view), k(index), rng(source), q0(view.q + index * IT), fresh(0), max_depth(0) {}
+
+	// the fused kernel's lanes integrate one trajectory after the other
+	__device__ __forceinline__ void rebind(int64_t index)
+	{
+		k = index;
+		q0 = e.q + index * IT;
+	}
 
 	// ---- global-memory accessors ---------------------------------------------------------------------------
 	// Noise memory: items of IT doubles in a ring of slots, [slot][B][IT]; a warp's 32 items of one slot are 32*IT*8

@@ -294,6 +294,51 @@ def test_ensemble_vs_oracle(name, B, T):
 	assert stats["n_overflow"] == 0
 
 
+@pytest.mark.parametrize("name,B,T", [("lorenz_additive", 1000, 0.5), ("lorenz_multiplicative", 700, 0.4), ("gbm", 999, 4.0)])
+def test_lane_recycling_small_grid(monkeypatch, name, B, T):
+	"""k_integrate with a grid of two blocks (256 lanes): every lane integrates several trajectories one after the other,
+	handing queued generator pairs and stream positions back and forth — results must not depend on that, within one
+	call, across calls, and for the sampling grid."""
+	monkeypatch.setenv("JSDE_RECYCLE", "1")
+	monkeypatch.setenv("JSDE_RESIDENT_BLOCKS", "2")
+	spec = models.ALL[name]
+	E, y0, seeds = make(spec, B)
+	stats = E.integrate(T)
+	ref = port.run_ensemble(spec, y0, seeds, 0.0, T)
+	assert_bits_equal(E.get_state(), ref["y"], name)
+	assert_bits_equal(E.t, ref["t"], name + " t")
+	_, acc, rej = E.controller_state()
+	assert (acc.astype(np.int64) == ref["accepted"]).all() and (rej.astype(np.int64) == ref["rejected"]).all()
+	assert stats["accepted"] == int(ref["accepted"].sum()) and stats["rejected"] == int(ref["rejected"].sum())
+	# second call continues every trajectory's stream; then a sampling grid in one launch
+	E.integrate(1.5 * T)
+	times = np.linspace(1.6 * T, 2.0 * T, 3)
+	grid = E.integrate_grid(times)
+	for k in range(0, B, 97):
+		P = port.PortCore(spec, y0[k], 0.0, int(seeds[k]))
+		P.integrate(T)
+		P.integrate(1.5 * T)
+		for j, tj in enumerate(times):
+			assert_bits_equal(grid[j, k], P.integrate(float(tj)), f"trajectory {k} sample {j}")
+
+
+def test_lane_recycling_with_jumps(monkeypatch):
+	monkeypatch.setenv("JSDE_RECYCLE", "1")
+	monkeypatch.setenv("JSDE_RESIDENT_BLOCKS", "1")
+	spec = models.lorenz_jumpy
+	B = 300
+	E, y0, seeds = make(spec, B)
+	taus, xis = jump_tape(B, 16)
+	E.integrate_jumps(1.0, taus, xis)
+	E.integrate_jumps(2.0, taus, xis)
+	y = E.get_state()
+	for k in range(0, B, 13):
+		P = port.PortCore(spec, y0[k], 0.0, int(seeds[k]))
+		P.integrate_jumps(1.0, taus[k], xis[k])
+		P.integrate_jumps(2.0, taus[k], xis[k])
+		assert_bits_equal(y[k], P.get_state(), f"trajectory {k}")
+
+
 def test_ragged_ensemble_size_and_single_trajectory():
 	"""B not a multiple of the block size, and B = 1 (the reference's own case)."""
 	spec = models.lorenz_additive
