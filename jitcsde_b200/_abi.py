@@ -55,7 +55,7 @@ ABI_SYMBOLS = (
 	"jsde_set_integration_parameters", "jsde_set_parameters", "jsde_pin_noise", "jsde_integrate", "jsde_integrate_jumps", "jsde_integrate_grid",
 	"jsde_get_state", "jsde_get_controller_state", "jsde_moments", "jsde_get_next_step", "jsde_get_p", "jsde_accept_step",
 	"jsde_apply_jump", "jsde_set_time", "jsde_draw_gauss_debug", "jsde_dump_noise", "jsde_measure_fp64_peak",
-	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_shared_div", "jsde_debug_inline_math", "jsde_last_error", "jsde_version",
+	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_shared_div", "jsde_debug_inline_math", "jsde_checkpoint_bytes", "jsde_checkpoint_save", "jsde_checkpoint_restore", "jsde_last_error", "jsde_version",
 )
 
 
@@ -89,6 +89,10 @@ def _declare(lib):
 	lib.jsde_debug_log.argtypes = [ctypes.c_int, c_double_p, c_double_p, ctypes.c_int64]
 	lib.jsde_debug_pow.argtypes = [ctypes.c_int, c_double_p, ctypes.c_double, c_double_p, ctypes.c_int64]
 	lib.jsde_debug_shared_div.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, c_u8_p, ctypes.c_int64]
+	lib.jsde_checkpoint_bytes.argtypes = [ctypes.c_void_p]
+	lib.jsde_checkpoint_bytes.restype = ctypes.c_int64
+	lib.jsde_checkpoint_save.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+	lib.jsde_checkpoint_restore.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
 	lib.jsde_debug_inline_math.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, c_u8_p, c_double_p, c_u8_p, ctypes.c_int64]
 	for name in ABI_SYMBOLS:
 		fn = getattr(lib, name)
@@ -291,6 +295,21 @@ class Ensemble:
 		out = np.empty((self.B, pairs, 2))
 		self._check(self.lib.jsde_draw_gauss_debug(self._h, float(scale), int(pairs), _dp(out)))
 		return out
+
+	def checkpoint(self) -> np.ndarray:
+		"""Everything needed to continue this ensemble bit for bit later (states, noise memory, generator states, controller,
+		counters, jump scheduling) as one uint8 array; see `jsde_checkpoint_save`."""
+		size = self.lib.jsde_checkpoint_bytes(self._h)
+		if size < 0:
+			raise JsdeError(self.lib.jsde_last_error().decode())
+		blob = np.empty(size, dtype=np.uint8)
+		self._check(self.lib.jsde_checkpoint_save(self._h, blob.ctypes.data_as(ctypes.c_void_p), size))
+		return blob
+
+	def restore(self, blob: np.ndarray) -> None:
+		"""Inverse of `checkpoint()` for an ensemble of the same model, size and noise capacity."""
+		blob = np.ascontiguousarray(blob, dtype=np.uint8)
+		self._check(self.lib.jsde_checkpoint_restore(self._h, blob.ctypes.data_as(ctypes.c_void_p), blob.size))
 
 	def dump_noise(self, b, max_items=64):
 		out = np.zeros((max_items, 1 + 2 * self.n))

@@ -310,6 +310,18 @@ class jitcsde:
 			warn("`number` does not appear to be a integer. This is very likely cause an error immediately.", stacklevel=2)
 		self.SDE.pin_noise(number, step_size)
 
+	def checkpoint(self):
+		"""The whole integrator state (states, times, step sizes, noise memory, every trajectory's generator state,
+		counters, jump scheduling, controller) as a uint8 array — for long campaigns (SURVEY.md §8 f item 4; the reference
+		has no counterpart).  `restore(blob)` on an instance with the same model and ensemble size continues bit for bit."""
+		self._initiate()
+		return self.SDE.checkpoint()
+
+	def restore(self, blob):
+		self._initiate()
+		self.SDE.restore(blob)
+		self._parameters_restored = True
+
 	def ensemble_moments(self, process_group=None, shift=None):
 		"""
 		Mean and variance of the current state over the whole ensemble.  With `torch.distributed` initialised the

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/jsde.h"
@@ -624,6 +625,95 @@ int jsde_dump_noise(jsde_t *h, int64_t b, double *out_host, int max_items, int *
 		const int64_t slot = (head + d) & h->v.Dmask;
 		CU(cudaMemcpy(out_host + (size_t)d * width, h->v.q + (slot * h->B + b) * noise_item_doubles(n), width * sizeof(double), cudaMemcpyDeviceToHost));
 	}
+	return JSDE_OK;
+}
+
+// ---- checkpoint / restore (SURVEY.md §8 f item 4) ---------------------------------------------------------------------
+// Everything a later jsde_integrate* needs to continue bit for bit: states, times, step sizes, the last proposal, the
+// noise memory, every trajectory's generator state with its queued pairs, statuses, counters, jump scheduling, the
+// controller, seeds and shared control parameters.  Per-trajectory parameters and jump tapes are inputs the caller
+// passes again.  Layout: header {magic, version, n, B, D, ring, CAP, additive} then the arrays in the order below.
+namespace {
+
+struct CheckpointHeader {
+	uint64_t magic;
+	int32_t version, n, additive, D, ring, cap, npar, reserved;
+	int64_t B;
+	Controller ctrl;
+	double first_step;
+};
+constexpr uint64_t CHECKPOINT_MAGIC = 0x4a53444543484b31ull;  // "JSDECHK1"
+
+std::vector<std::pair<void *, size_t>> checkpoint_sections(jsde_handle *h)
+{
+	const size_t B = (size_t)h->B, n = Model::N, ring = (size_t)h->v.Dmask + 1;
+	EnsembleView &v = h->v;
+	return {
+		{v.y, B * n * 8}, {v.t, B * 8}, {v.dt, B * 8}, {v.new_y, B * n * 8}, {v.err, B * n * 8}, {v.new_t, B * 8},
+		{v.q, ring * B * noise_item_doubles((int)n) * 8}, {v.q_count, B * 4}, {v.q_cursor, B * 4}, {v.q_head, B * 4},
+		{v.mt, B * MT_CHUNKS * sizeof(uint4)}, {v.mt_chunk, B * 4},
+		{v.rng_spill, (size_t)WarpRng<Model::N>::CAP * 3 * B * 8}, {v.rng_level, B * 4},
+		{v.status, B * 4}, {v.accepted, B * 8}, {v.rejected, B * 8},
+		{v.next_jump, B * 8}, {v.jump_set, B}, {v.tape_pos, B * 8},
+		{h->seeds, B * 4}, {h->par, (size_t)(Model::NPAR > 0 ? Model::NPAR : 1) * 8},
+	};
+}
+
+}  // namespace
+
+int64_t jsde_checkpoint_bytes(jsde_t *h)
+{
+	if (!h)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	size_t total = sizeof(CheckpointHeader);
+	for (auto &s : checkpoint_sections(h))
+		total += s.second;
+	return (int64_t)total;
+}
+
+int jsde_checkpoint_save(jsde_t *h, void *blob_host, int64_t bytes)
+{
+	if (!h || !blob_host || bytes != jsde_checkpoint_bytes(h))
+		return fail(JSDE_E_ARG, "Wrong input. (checkpoint buffer size)");
+	int rc = bind(h);
+	if (rc) return rc;
+	CheckpointHeader hd{};
+	hd.magic = CHECKPOINT_MAGIC; hd.version = 1; hd.n = Model::N; hd.additive = Model::ADDITIVE; hd.D = h->D; hd.ring = h->v.Dmask + 1;
+	hd.cap = WarpRng<Model::N>::CAP; hd.npar = Model::NPAR; hd.B = h->B; hd.ctrl = h->ctrl; hd.first_step = h->first_step;
+	char *out = static_cast<char *>(blob_host);
+	memcpy(out, &hd, sizeof(hd));
+	out += sizeof(hd);
+	CU(cudaStreamSynchronize(h->stream));
+	for (auto &s : checkpoint_sections(h)) {
+		CU(cudaMemcpyAsync(out, s.first, s.second, cudaMemcpyDeviceToHost, h->stream));
+		out += s.second;
+	}
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_checkpoint_restore(jsde_t *h, const void *blob_host, int64_t bytes)
+{
+	if (!h || !blob_host || bytes != jsde_checkpoint_bytes(h))
+		return fail(JSDE_E_ARG, "Wrong input. (checkpoint buffer size)");
+	CheckpointHeader hd;
+	const char *in = static_cast<const char *>(blob_host);
+	memcpy(&hd, in, sizeof(hd));
+	in += sizeof(hd);
+	if (hd.magic != CHECKPOINT_MAGIC || hd.version != 1 || hd.n != Model::N || hd.additive != (int)Model::ADDITIVE || hd.B != h->B ||
+		hd.D != h->D || hd.ring != h->v.Dmask + 1 || hd.cap != WarpRng<Model::N>::CAP || hd.npar != Model::NPAR)
+		return fail(JSDE_E_ARG, "Wrong input. (checkpoint belongs to a different model or ensemble shape)");
+	int rc = bind(h);
+	if (rc) return rc;
+	h->ctrl = hd.ctrl;
+	h->first_step = hd.first_step;
+	for (auto &s : checkpoint_sections(h)) {
+		CU(cudaMemcpyAsync(s.first, in, s.second, cudaMemcpyHostToDevice, h->stream));
+		in += s.second;
+	}
+	h->v.par = h->par;  // shared parameters are part of the checkpoint; per-trajectory ones are set again by the caller
+	h->v.par_stride = 0;
+	CU(cudaStreamSynchronize(h->stream));
 	return JSDE_OK;
 }
 

@@ -391,6 +391,9 @@ int jsde_debug_log(int, const double *, double *, int64_t) { return unsupported(
 int jsde_debug_pow(int, const double *, double, double *, int64_t) { return unsupported("debug_pow"); }
 int jsde_debug_shared_div(int, const double *, const double *, double *, unsigned char *, int64_t) { return unsupported("debug_shared_div"); }
 int jsde_debug_inline_math(int, const double *, const double *, double *, unsigned char *, double *, unsigned char *, int64_t) { return unsupported("debug_inline_math"); }
+int64_t jsde_checkpoint_bytes(jsde_t *) { return unsupported("checkpoints"); }
+int jsde_checkpoint_save(jsde_t *, void *, int64_t) { return unsupported("checkpoints"); }
+int jsde_checkpoint_restore(jsde_t *, const void *, int64_t) { return unsupported("checkpoints"); }
 
 int jsde_measure_fp64_peak(int device, double *tflops)
 {

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from jitcsde_b200 import _abi, models
-from jitcsde_b200._abi import ControllerParameters, Ensemble
+from jitcsde_b200._abi import ControllerParameters, Ensemble, JsdeError
 from oracle import port
 from util import assert_bits_equal, ensemble_inputs, golden, jump_tape, unhex
 
@@ -337,6 +337,33 @@ def test_lane_recycling_with_jumps(monkeypatch):
 		P.integrate_jumps(1.0, taus[k], xis[k])
 		P.integrate_jumps(2.0, taus[k], xis[k])
 		assert_bits_equal(y[k], P.get_state(), f"trajectory {k}")
+
+
+@pytest.mark.parametrize("name", ["lorenz_additive", "lorenz_multiplicative"])
+def test_checkpoint_restore_continues_bit_for_bit(name):
+	"""save -> integrate on -> restore (into a second handle, too) -> integrate on: the same bits, incl. a pending
+	rejected proposal's noise and queued generator pairs."""
+	spec = models.ALL[name]
+	B = 300
+	E, y0, seeds = make(spec, B)
+	E.integrate(0.37)
+	blob = E.checkpoint()
+	E.integrate(0.9)
+	want_y, want_t = E.get_state(), E.t.copy()
+	want_dt, want_acc, want_rej = E.controller_state()
+	E.restore(blob)
+	E.integrate(0.9)
+	assert_bits_equal(E.get_state(), want_y, "restored in place")
+	F = Ensemble(spec, B)  # a fresh handle (never seeded) continues from the blob
+	F.restore(blob)
+	F.integrate(0.9)
+	assert_bits_equal(F.get_state(), want_y, "restored into a fresh handle")
+	assert_bits_equal(F.t, want_t, "times")
+	dt, acc, rej = F.controller_state()
+	assert_bits_equal(dt, want_dt, "step sizes")
+	assert (acc == want_acc).all() and (rej == want_rej).all()
+	with pytest.raises(JsdeError, match="checkpoint"):
+		Ensemble(spec, B + 1).restore(blob)
 
 
 def test_ragged_ensemble_size_and_single_trajectory():
