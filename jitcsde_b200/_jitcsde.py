@@ -320,7 +320,6 @@ class jitcsde:
 	def restore(self, blob):
 		self._initiate()
 		self.SDE.restore(blob)
-		self._parameters_restored = True
 
 	def ensemble_moments(self, process_group=None, shift=None):
 		"""
