@@ -28,11 +28,12 @@
 // Both loops leave on the same published mask == 0.  The producer owns the persistence of queued pairs between
 // launches (same spill format as WarpRng, which the single-step kernels use).
 //
-// Trajectory recycling: the grid is at most one wave of blocks; a lane whose trajectory is done takes the next one
-// from a pool (atomic counter) instead of idling until its warp's and block's slowest trajectory finishes (7 % of the
-// headline run).  The consumer announces the change through `swap[lane]` together with the final popped count of the
-// old trajectory; the producer then spills the old trajectory's queued pairs and stream position, loads the new
-// one's, and refills — the lane sits out that one round.
+// Trajectory recycling (kernels.cuh, RECYCLE): the grid is at most one wave of blocks; a lane whose trajectory is done
+// takes the next one from a pool (atomic counter) instead of idling until its warp's and block's slowest trajectory
+// finishes (+26 % on SRI-Lorenz, whose step counts differ by tens of per cent between trajectories).  The consumer
+// announces the change through `swap[lane]` together with the final popped count of the old trajectory; the producer
+// then spills the old trajectory's queued pairs and stream position, loads the new one's, and refills — the lane sits
+// out that one round.  Every lane's first trajectory arrives the same way (round 0).
 #pragma once
 
 #include "warp_rng.cuh"
