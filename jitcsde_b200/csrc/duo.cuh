@@ -42,15 +42,28 @@ namespace jsde {
 
 constexpr int DUO_PAIRS = 4;
 constexpr int DUO_BLOCK = 64 * DUO_PAIRS;
-#ifndef JSDE_DUO_MIN_BLOCKS
-#define JSDE_DUO_MIN_BLOCKS 3
+// Resident blocks per SM and the register split between the warpgroups (the launch allocation 65536/(256*blocks),
+// rounded down to a multiple of 8, is redistributed by setmaxnreg: consumer + producer = 2 x allocation).  Up to three
+// components the stepper fits 104 registers and three blocks are resident; beyond that it would spill, so two blocks
+// with 168/88.  (Measured for n = 3: 112/48 and the two-block splits are 5-8 % slower.)  The macros override.
+template <int N>
+struct DuoConfig {
+#ifdef JSDE_DUO_MIN_BLOCKS
+	static constexpr int BLOCKS = JSDE_DUO_MIN_BLOCKS;
+#else
+	static constexpr int BLOCKS = N <= 3 ? 3 : 2;
 #endif
-#ifndef JSDE_DUO_CONSUMER_REGS
-#define JSDE_DUO_CONSUMER_REGS 104
+#ifdef JSDE_DUO_CONSUMER_REGS
+	static constexpr int CONSUMER_REGS = JSDE_DUO_CONSUMER_REGS;
+#else
+	static constexpr int CONSUMER_REGS = N <= 3 ? 104 : 168;
 #endif
-#ifndef JSDE_DUO_PRODUCER_REGS
-#define JSDE_DUO_PRODUCER_REGS 56
+#ifdef JSDE_DUO_PRODUCER_REGS
+	static constexpr int PRODUCER_REGS = JSDE_DUO_PRODUCER_REGS;
+#else
+	static constexpr int PRODUCER_REGS = N <= 3 ? 56 : 88;
 #endif
+};
 #ifndef JSDE_DUO_STAGE_AHEAD
 #define JSDE_DUO_STAGE_AHEAD 2  // slots whose generator words are in flight (cp.async) ahead of the one being processed
 #endif

@@ -47,6 +47,15 @@ ou = ModelSpec("ou", 2, True, ("-1.0*y(0)", "-0.5*(y(1)-1.0)"), ("0.3", "0.2"))
 #: time-dependent additive noise (exercises the g(t+h) / g(t) evaluation order of `jitced_template.c:476,485`)
 ou_timedep = ModelSpec("ou_timedep", 2, True, ("-1.0*y(0)+t", "-0.5*(y(1)-1.0)"), ("0.3*(1.0+t)", "0.2/(1.0+t*t)"))
 
+#: six coupled components, additive: the lane kernels beyond the 1-3 components of the benchmark configurations (register
+#: and shared-memory budgets scale with n)
+ring6 = ModelSpec("ring6", 6, True, tuple(f"-1.0*y({i})+0.5*(y({(i + 1) % 6})-y({(i + 5) % 6}))" for i in range(6)),
+	("0.1", "0.2", "0.3", "0.1", "0.2", "0.3"))
+
+#: the same ring with multiplicative noise (SRI with six components)
+ring6_mult = ModelSpec("ring6_mult", 6, False, tuple(f"-1.0*y({i})+0.5*(y({(i + 1) % 6})-y({(i + 5) % 6}))" for i in range(6)),
+	tuple(f"0.1*y({i})+0.05" for i in range(6)))
+
 #: scalar validation SDE of `tests/validation.py:21-32` without the exponential (polynomial part only)
 cubic = ModelSpec("cubic", 1, True, ("-(y(0)*y(0)*y(0))+4*y(0)+y(0)*y(0)",), ("3.0",))
 
@@ -93,5 +102,5 @@ def fhn_1000() -> ModelSpec:
 
 ALL = {m.name: m for m in (
 	lorenz_additive, lorenz_additive_fixture, lorenz_multiplicative, lorenz_jumpy,
-	gbm, gbm_pars, duffing, ou, ou_timedep, cubic, fhn_small,
+	gbm, gbm_pars, duffing, ou, ou_timedep, cubic, ring6, ring6_mult, fhn_small,
 )}

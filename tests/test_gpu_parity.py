@@ -280,6 +280,7 @@ def test_jump_golden():
 @pytest.mark.parametrize("name,B,T", [
 	("lorenz_additive", 512, 1.0), ("lorenz_multiplicative", 256, 1.0), ("gbm", 512, 10.0), ("duffing", 256, 5.0),
 	("ou", 256, 5.0), ("ou_timedep", 128, 3.0), ("lorenz_additive_fixture", 128, 2.0), ("cubic", 128, 2.0),
+	("ring6", 200, 2.0), ("ring6_mult", 200, 1.0),
 ])
 def test_ensemble_vs_oracle(name, B, T):
 	spec = models.ALL[name]
