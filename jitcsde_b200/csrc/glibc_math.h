@@ -45,6 +45,81 @@ static inline double jsde_asd_(uint64_t u) { double x; memcpy(&x, &u, 8); return
 
 #include "glibc_tables.h"
 
+#if defined(__CUDACC__) && !defined(JSDE_LITERAL_COEFFICIENTS)
+// Device build: the scalar coefficients come from constant memory, so that every DFMA/DMUL takes them as a c[bank][offset]
+// operand.  As literals each 64-bit coefficient costs two move instructions per use (no FP64 immediates): 104 + 81 of
+// the fused kernel's stepper instructions were such moves.
+static __constant__ double JSDE_COEFFICIENTS[] = {
+	JSDE_LN2HI, JSDE_LN2LO, JSDE_EXP_INVLN2N, JSDE_EXP_SHIFT, JSDE_EXP_NEGLN2HIN, JSDE_EXP_NEGLN2LON, JSDE_LOG_A0, JSDE_LOG_A1, JSDE_LOG_A2, JSDE_LOG_A3, JSDE_LOG_A4, JSDE_LOG_B0, JSDE_LOG_B1, JSDE_LOG_B2, JSDE_LOG_B3, JSDE_LOG_B4, JSDE_LOG_B5, JSDE_LOG_B6, JSDE_LOG_B7, JSDE_LOG_B8, JSDE_LOG_B9, JSDE_LOG_B10, JSDE_POW_A0, JSDE_POW_A1, JSDE_POW_A2, JSDE_POW_A3, JSDE_POW_A4, JSDE_POW_A5, JSDE_POW_A6, JSDE_EXP_C2, JSDE_EXP_C3, JSDE_EXP_C4, JSDE_EXP_C5
+};
+#undef JSDE_LN2HI
+#define JSDE_LN2HI (JSDE_COEFFICIENTS[0])
+#undef JSDE_LN2LO
+#define JSDE_LN2LO (JSDE_COEFFICIENTS[1])
+#undef JSDE_EXP_INVLN2N
+#define JSDE_EXP_INVLN2N (JSDE_COEFFICIENTS[2])
+#undef JSDE_EXP_SHIFT
+#define JSDE_EXP_SHIFT (JSDE_COEFFICIENTS[3])
+#undef JSDE_EXP_NEGLN2HIN
+#define JSDE_EXP_NEGLN2HIN (JSDE_COEFFICIENTS[4])
+#undef JSDE_EXP_NEGLN2LON
+#define JSDE_EXP_NEGLN2LON (JSDE_COEFFICIENTS[5])
+#undef JSDE_LOG_A0
+#define JSDE_LOG_A0 (JSDE_COEFFICIENTS[6])
+#undef JSDE_LOG_A1
+#define JSDE_LOG_A1 (JSDE_COEFFICIENTS[7])
+#undef JSDE_LOG_A2
+#define JSDE_LOG_A2 (JSDE_COEFFICIENTS[8])
+#undef JSDE_LOG_A3
+#define JSDE_LOG_A3 (JSDE_COEFFICIENTS[9])
+#undef JSDE_LOG_A4
+#define JSDE_LOG_A4 (JSDE_COEFFICIENTS[10])
+#undef JSDE_LOG_B0
+#define JSDE_LOG_B0 (JSDE_COEFFICIENTS[11])
+#undef JSDE_LOG_B1
+#define JSDE_LOG_B1 (JSDE_COEFFICIENTS[12])
+#undef JSDE_LOG_B2
+#define JSDE_LOG_B2 (JSDE_COEFFICIENTS[13])
+#undef JSDE_LOG_B3
+#define JSDE_LOG_B3 (JSDE_COEFFICIENTS[14])
+#undef JSDE_LOG_B4
+#define JSDE_LOG_B4 (JSDE_COEFFICIENTS[15])
+#undef JSDE_LOG_B5
+#define JSDE_LOG_B5 (JSDE_COEFFICIENTS[16])
+#undef JSDE_LOG_B6
+#define JSDE_LOG_B6 (JSDE_COEFFICIENTS[17])
+#undef JSDE_LOG_B7
+#define JSDE_LOG_B7 (JSDE_COEFFICIENTS[18])
+#undef JSDE_LOG_B8
+#define JSDE_LOG_B8 (JSDE_COEFFICIENTS[19])
+#undef JSDE_LOG_B9
+#define JSDE_LOG_B9 (JSDE_COEFFICIENTS[20])
+#undef JSDE_LOG_B10
+#define JSDE_LOG_B10 (JSDE_COEFFICIENTS[21])
+#undef JSDE_POW_A0
+#define JSDE_POW_A0 (JSDE_COEFFICIENTS[22])
+#undef JSDE_POW_A1
+#define JSDE_POW_A1 (JSDE_COEFFICIENTS[23])
+#undef JSDE_POW_A2
+#define JSDE_POW_A2 (JSDE_COEFFICIENTS[24])
+#undef JSDE_POW_A3
+#define JSDE_POW_A3 (JSDE_COEFFICIENTS[25])
+#undef JSDE_POW_A4
+#define JSDE_POW_A4 (JSDE_COEFFICIENTS[26])
+#undef JSDE_POW_A5
+#define JSDE_POW_A5 (JSDE_COEFFICIENTS[27])
+#undef JSDE_POW_A6
+#define JSDE_POW_A6 (JSDE_COEFFICIENTS[28])
+#undef JSDE_EXP_C2
+#define JSDE_EXP_C2 (JSDE_COEFFICIENTS[29])
+#undef JSDE_EXP_C3
+#define JSDE_EXP_C3 (JSDE_COEFFICIENTS[30])
+#undef JSDE_EXP_C4
+#define JSDE_EXP_C4 (JSDE_COEFFICIENTS[31])
+#undef JSDE_EXP_C5
+#define JSDE_EXP_C5 (JSDE_COEFFICIENTS[32])
+#endif
+
 // ---- log --------------------------------------------------------------------------------------------------
 // glibc splits on |x-1|: inputs in [1-2^-4, 1+0x1.09p-4) take a table-free polynomial, everything else the table
 // path.  The two halves are exposed separately so that a SIMT caller can run the (long, rare: 6 % of polar radii)
