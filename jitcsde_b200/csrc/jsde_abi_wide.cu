@@ -101,25 +101,47 @@ int reset_integrator(jsde_handle *h)
 // One block integrates `tpb` trajectories (wide.cuh).  tpb is chosen so that the ensemble fills the GPU's block slots
 // (2 blocks per SM) in one wave where possible: 2^11 trajectories on 148 SMs -> 7 per block, 293 blocks on 296 slots.
 template <int T>
-int launch_one(jsde_handle *h, double target_time)
+int launch_one(jsde_handle *h, double target_time, const double *grid_times, int grid_count, double *grid_out)
 {
 	const size_t smem = wide_smem_bytes<Model, T>();
 	CU(cudaFuncSetAttribute(k_wide_integrate<Model, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_wide_integrate<Model, T><<<grid_for(h->B, T), WBLOCK, smem, h->stream>>>(h->v, h->ctrl, target_time);
+	k_wide_integrate<Model, T><<<grid_for(h->B, T), WBLOCK, smem, h->stream>>>(h->v, h->ctrl, target_time, grid_times, grid_count, grid_out);
 	CU(cudaGetLastError());
 	return JSDE_OK;
 }
 
-int launch_integrate(jsde_handle *h, double target_time)
+int launch_integrate(jsde_handle *h, double target_time, const double *grid_times = nullptr, int grid_count = 0, double *grid_out = nullptr)
 {
 	switch (h->tpb) {
-	case 1: return launch_one<1>(h, target_time);
-	case 2: return launch_one<2>(h, target_time);
-	case 4: return launch_one<4>(h, target_time);
-	case 6: return launch_one<6>(h, target_time);
-	case 7: return launch_one<7>(h, target_time);
-	default: return launch_one<8>(h, target_time);
+	case 1: return launch_one<1>(h, target_time, grid_times, grid_count, grid_out);
+	case 2: return launch_one<2>(h, target_time, grid_times, grid_count, grid_out);
+	case 4: return launch_one<4>(h, target_time, grid_times, grid_count, grid_out);
+	case 6: return launch_one<6>(h, target_time, grid_times, grid_count, grid_out);
+	case 7: return launch_one<7>(h, target_time, grid_times, grid_count, grid_out);
+	default: return launch_one<8>(h, target_time, grid_times, grid_count, grid_out);
 	}
+}
+
+int read_totals(jsde_handle *h, jsde_stats *stats_host)
+{
+	CallTotals tot;
+	CU(cudaEventRecord(h->ev1, h->stream));
+	CU(cudaMemcpyAsync(&tot, h->v.totals, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	if (stats_host) {
+		float ms = 0.f;
+		CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+		stats_host->accepted = tot.accepted;
+		stats_host->rejected = tot.rejected;
+		stats_host->fresh_draws = tot.fresh_draws;
+		stats_host->jumps = 0;
+		stats_host->n_min_step = tot.n_min_step;
+		stats_host->n_overflow = tot.n_overflow;
+		stats_host->max_noise_depth = tot.max_depth;
+		stats_host->kernel_launches = 1;
+		stats_host->kernel_ms = ms;
+	}
+	return JSDE_OK;
 }
 
 int choose_tpb(int device, int64_t B)
@@ -300,23 +322,39 @@ int jsde_integrate(jsde_t *h, double target_time, jsde_stats *stats_host)
 	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
 	CU(cudaEventRecord(h->ev0, h->stream));
 	if ((rc = launch_integrate(h, target_time))) return rc;
-	CallTotals tot;
-	CU(cudaEventRecord(h->ev1, h->stream));
-	CU(cudaMemcpyAsync(&tot, h->v.totals, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
-	CU(cudaStreamSynchronize(h->stream));
-	if (stats_host) {
-		float ms = 0.f;
-		CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-		stats_host->accepted = tot.accepted;
-		stats_host->rejected = tot.rejected;
-		stats_host->fresh_draws = tot.fresh_draws;
-		stats_host->jumps = 0;
-		stats_host->n_min_step = tot.n_min_step;
-		stats_host->n_overflow = tot.n_overflow;
-		stats_host->max_noise_depth = tot.max_depth;
-		stats_host->kernel_launches = 1;
-		stats_host->kernel_ms = ms;
+	return read_totals(h, stats_host);
+}
+
+// the caller's sampling loop `for time in times: integrate(time)` (examples/noisy_lorenz.py:95-96) in one launch;
+// y_host [n_times][B][n]
+int jsde_integrate_grid(jsde_t *h, const double *times_host, int64_t n_times, const jsde_jump_tape *tape, double *y_host, jsde_stats *stats_host)
+{
+	if (!h || !times_host || n_times <= 0 || n_times > 0x7fffffff || !y_host)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	if (tape)
+		return unsupported("jumps");
+	for (int64_t j = 0; j < n_times; j++)
+		if (!(times_host[j] == times_host[j]))
+			return fail(JSDE_E_ARG, "Wrong input. (sample time is NaN)");
+	int rc = bind(h);
+	if (rc) return rc;
+	const size_t count = (size_t)n_times * (size_t)h->B * Model::N;
+	double *times = nullptr, *out = nullptr;
+	CU(cudaMalloc(&times, n_times * sizeof(double)));
+	if (cudaMalloc(&out, count * sizeof(double)) != cudaSuccess) {
+		cudaFree(times);
+		return fail(JSDE_E_NOMEM, "sampling grid does not fit in device memory: n_times*B*n doubles");
 	}
+	auto cleanup = [&]() { cudaFree(times); cudaFree(out); };
+	cudaError_t err = cudaMemcpyAsync(times, times_host, n_times * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+	if (err == cudaSuccess) err = cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream);
+	if (err == cudaSuccess) err = cudaEventRecord(h->ev0, h->stream);
+	if (err != cudaSuccess) { cleanup(); return fail(JSDE_E_CUDA, cudaGetErrorString(err)); }
+	if ((rc = launch_integrate(h, times_host[n_times - 1], times, (int)n_times, out)) || (rc = read_totals(h, stats_host))) { cleanup(); return rc; }
+	err = cudaMemcpy(y_host, out, count * sizeof(double), cudaMemcpyDeviceToHost);
+	cleanup();
+	if (err != cudaSuccess)
+		return fail(JSDE_E_CUDA, cudaGetErrorString(err));
 	return JSDE_OK;
 }
 
@@ -380,7 +418,6 @@ int jsde_set_time(jsde_t *h, const double *t_host)
 
 int jsde_pin_noise(jsde_t *, unsigned, double) { return unsupported("pin_noise"); }
 int jsde_integrate_jumps(jsde_t *, double, const jsde_jump_tape *, jsde_stats *) { return unsupported("jumps"); }
-int jsde_integrate_grid(jsde_t *, const double *, int64_t, const jsde_jump_tape *, double *, jsde_stats *) { return unsupported("the sampling grid"); }
 int jsde_get_next_step(jsde_t *, const double *) { return unsupported("the single-step surface"); }
 int jsde_get_p(jsde_t *, double, double, double *) { return unsupported("the single-step surface"); }
 int jsde_accept_step(jsde_t *, const uint8_t *) { return unsupported("the single-step surface"); }

@@ -23,7 +23,7 @@
 //   noise memory ..... jitced_template.c:170-250; items are addressed through a small permutation (logical position ->
 //                      physical slot) so that a Brownian-bridge insertion or a pop never moves 16 KB items.
 //   SRA1 step ........ jitced_template.c:466-494;   error ratio / commit ... :502-536;   controller ... _jitcsde.py:569-630
-// Additive noise only (the network of config 5); no jumps, no sampling grid yet.
+// Additive noise only (the network of config 5); no jumps yet.
 #pragma once
 
 #include "ensemble.cuh"
@@ -80,9 +80,10 @@ struct TrajShared {
 	double qh[MAX_DEPTH];
 	int order[MAX_DEPTH];
 	double warp_max[WWARPS];
-	double t, dt, h;
+	double t, dt, h, target;
 	int pos, count, cursor, status, running, last, accept, max_depth;
 	unsigned acc, rej, fresh;
+	int grid_index, sample_slot;  // sampling-grid mode: next sample time, and (>= 0) the sample the commit phase records
 	int pad_;
 };
 
@@ -191,8 +192,12 @@ constexpr size_t wide_smem_bytes()
 	return (size_t)(Model::UNITS > 0 ? Model::UNITS : 1) * TPAD * sizeof(double) + (size_t)T * sizeof(TrajShared);
 }
 
+// Sampling-grid mode (grid_times != nullptr): every trajectory integrates to grid_times[0], records its state in
+// grid_out[0][b][·], goes on to grid_times[1], … — the sequence of integrate() calls of examples/noisy_lorenz.py:95-96
+// (truncated last step + Brownian bridge at every sample time) in one launch.
 template <class Model, int T>
-__global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Controller c, double target)
+__global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Controller c, double target,
+	const double *__restrict__ grid_times, int grid_count, double *__restrict__ grid_out)
 {
 	static_assert(T >= 1 && T <= TMAX && T <= WWARPS, "one warp per trajectory");
 	constexpr int N = Model::N;
@@ -228,7 +233,11 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 				if (status == TRAJ_MIN_STEP)
 					status = TRAJ_OK;  // the reference raises once per call and lets the caller carry on (_jitcsde.py:569-579)
 				S.status = status;
-				S.running = status == TRAJ_OK && !(S.t >= target);  // integrate() with nothing to do (:614)
+				S.target = grid_times ? grid_times[0] : target;
+				S.grid_index = 0;
+				S.sample_slot = -1;
+				// integrate() with nothing to do (:614) returns at once; in grid mode that is decided per sample in P1
+				S.running = status == TRAJ_OK && (grid_times != nullptr || !(S.t >= target));
 				S.acc = S.rej = S.fresh = 0;
 				S.max_depth = 0;
 				S.cursor = 0;
@@ -237,6 +246,7 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 		} else if (lane == 0) {
 			S.running = 0;
 			S.accept = 0;
+			S.sample_slot = -1;
 			S.status = TRAJ_OK;
 			S.acc = S.rej = S.fresh = 0;
 			S.max_depth = 0;
@@ -262,12 +272,34 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			double *const qw = e.qw + b * D * 2 * N;
 			double *const sW = e.sW + b * N, *const sZ = e.sZ + b * N;
 			const double t = S.t, dt = S.dt;
+			double goal = S.target;
+			if (grid_times) {  // sample times that are already reached: record the state as it is (integrate() is a no-op)
+				int gi = S.grid_index;
+				while (gi < grid_count && t >= goal) {
+					const double *Y = e.y + b * N;
+					double *out = grid_out + ((int64_t)gi * e.B + b) * N;
+					for (int i = lane; i < N; i += 32)
+						out[i] = Y[i];
+					gi++;
+					if (gi < grid_count)
+						goal = grid_times[gi];
+				}
+				__syncwarp();
+				if (lane == 0) {
+					S.grid_index = gi;
+					S.target = goal;
+					if (gi >= grid_count)
+						S.running = 0;
+				}
+				__syncwarp();
+			}
+			if (S.running) {
 			double h;
 			bool last = false;
-			if (t + dt < target)
+			if (t + dt < goal)
 				h = dt;
 			else {
-				h = target - t;
+				h = goal - t;
 				last = true;
 			}
 			int count = S.count, pos = S.pos;
@@ -386,6 +418,7 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 					S.cursor = cur;
 					S.max_depth = count > S.max_depth ? count : S.max_depth;
 				}
+			}
 			}
 		}
 		__syncthreads();
@@ -530,8 +563,17 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 					S.t = S.t + h;
 					S.acc++;
 					S.accept = 1;
-					if (S.last)
-						S.running = 0;
+					if (S.last) {
+						if (grid_times) {  // the commit phase records this sample; then on to the next sample time
+							S.sample_slot = S.grid_index;
+							S.grid_index++;
+							if (S.grid_index < grid_count)
+								S.target = grid_times[S.grid_index];
+							else
+								S.running = 0;
+						} else
+							S.running = 0;
+					}
 				}
 				S.dt = dt;
 			}
@@ -543,12 +585,19 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			if (!ts[tr].accept)
 				continue;
 			const int64_t b = b0 + tr;
-			for (int i = tid; i < N; i += WBLOCK)
-				e.y[b * N + i] = e.sNY[b * N + i];
+			const int slot = ts[tr].sample_slot;
+			for (int i = tid; i < N; i += WBLOCK) {
+				const double v = e.sNY[b * N + i];
+				e.y[b * N + i] = v;
+				if (slot >= 0)
+					grid_out[((int64_t)slot * e.B + b) * N + i] = v;
+			}
 		}
 		__syncthreads();
-		if (tid < T)
+		if (tid < T) {
 			ts[tid].accept = 0;
+			ts[tid].sample_slot = -1;
+		}
 		__syncthreads();
 	}
 

@@ -55,6 +55,30 @@ def test_config5_network_n1000_vs_oracle(monkeypatch, tpb, B):
 	assert (E.status == 0).all()
 
 
+@pytest.mark.parametrize("tpb", [1, 7])
+def test_wide_sampling_grid_equals_repeated_calls(monkeypatch, tpb):
+	"""integrate_grid (one launch) == the loop of integrate() calls, bit for bit, incl. repeated and already-passed
+	sample times; and == the oracle."""
+	monkeypatch.setenv("JSDE_WIDE_TPB", str(tpb))
+	spec = models.fhn_small
+	B = 19
+	times = np.array([0.0, 0.25, 0.25, 0.6, 1.3, 1.3001, 2.0])
+	E, _, y0 = run(spec, B, 0.0)
+	grid = E.integrate_grid(times)
+	F, _, _ = run(spec, B, 0.0)
+	for j, tj in enumerate(times):
+		F.integrate(float(tj))
+		assert_bits_equal(grid[j], F.get_state(), f"sample {j}")
+	assert_bits_equal(E.get_state(), F.get_state(), "final state")
+	assert_bits_equal(E.t, F.t, "times")
+	P = port.PortCore(spec, y0[3], 0.0, 3)
+	for j, tj in enumerate(times):
+		assert_bits_equal(grid[j, 3], P.integrate(float(tj)), f"oracle, sample {j}")
+	E.integrate(2.5)  # and the call after a grid continues normally
+	F.integrate(2.5)
+	assert_bits_equal(E.get_state(), F.get_state(), "continued")
+
+
 def test_wide_failure_paths_and_unsupported_calls():
 	spec = models.fhn_small
 	E, stats, _ = run(spec, 4, 1.0, min_step=10.0, max_step=10.0, first_step=10.0)
