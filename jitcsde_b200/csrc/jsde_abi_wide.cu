@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/jsde.h"
@@ -428,9 +429,81 @@ int jsde_debug_log(int, const double *, double *, int64_t) { return unsupported(
 int jsde_debug_pow(int, const double *, double, double *, int64_t) { return unsupported("debug_pow"); }
 int jsde_debug_shared_div(int, const double *, const double *, double *, unsigned char *, int64_t) { return unsupported("debug_shared_div"); }
 int jsde_debug_inline_math(int, const double *, const double *, double *, unsigned char *, double *, unsigned char *, int64_t) { return unsupported("debug_inline_math"); }
-int64_t jsde_checkpoint_bytes(jsde_t *) { return unsupported("checkpoints"); }
-int jsde_checkpoint_save(jsde_t *, void *, int64_t) { return unsupported("checkpoints"); }
-int jsde_checkpoint_restore(jsde_t *, const void *, int64_t) { return unsupported("checkpoints"); }
+// ---- checkpoint / restore: same contract as the lane library (include/jsde.h) ----------------------------------------
+namespace {
+struct WideCheckpointHeader {
+	uint64_t magic;
+	int32_t version, n, D, npar;
+	int64_t B;
+	Controller ctrl;
+	double first_step;
+};
+constexpr uint64_t WIDE_CHECKPOINT_MAGIC = 0x4a53444557434b31ull;  // "JSDEWCK1"
+
+std::vector<std::pair<void *, size_t>> checkpoint_sections(jsde_handle *h)
+{
+	const size_t B = (size_t)h->B, n = Model::N, D = (size_t)h->D;
+	WideView &v = h->v;
+	return {
+		{v.y, B * n * 8}, {v.t, B * 8}, {v.dt, B * 8}, {v.qh, B * D * 8}, {v.qw, B * D * 2 * n * 8}, {v.order, B * D * 4},
+		{v.q_count, B * 4}, {v.key, B * MT_WORDS * 4}, {v.pos, B * 4}, {v.status, B * 4}, {v.accepted, B * 8}, {v.rejected, B * 8},
+		{h->seeds, B * 4}, {h->par, (size_t)(Model::NPAR > 0 ? Model::NPAR : 1) * 8},
+	};
+}
+}  // namespace
+
+int64_t jsde_checkpoint_bytes(jsde_t *h)
+{
+	if (!h)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	size_t total = sizeof(WideCheckpointHeader);
+	for (auto &s : checkpoint_sections(h))
+		total += s.second;
+	return (int64_t)total;
+}
+
+int jsde_checkpoint_save(jsde_t *h, void *blob_host, int64_t bytes)
+{
+	if (!h || !blob_host || bytes != jsde_checkpoint_bytes(h))
+		return fail(JSDE_E_ARG, "Wrong input. (checkpoint buffer size)");
+	int rc = bind(h);
+	if (rc) return rc;
+	WideCheckpointHeader hd{};
+	hd.magic = WIDE_CHECKPOINT_MAGIC; hd.version = 1; hd.n = Model::N; hd.D = h->D; hd.npar = Model::NPAR; hd.B = h->B;
+	hd.ctrl = h->ctrl; hd.first_step = h->first_step;
+	char *out = static_cast<char *>(blob_host);
+	memcpy(out, &hd, sizeof(hd));
+	out += sizeof(hd);
+	CU(cudaStreamSynchronize(h->stream));
+	for (auto &s : checkpoint_sections(h)) {
+		CU(cudaMemcpyAsync(out, s.first, s.second, cudaMemcpyDeviceToHost, h->stream));
+		out += s.second;
+	}
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_checkpoint_restore(jsde_t *h, const void *blob_host, int64_t bytes)
+{
+	if (!h || !blob_host || bytes != jsde_checkpoint_bytes(h))
+		return fail(JSDE_E_ARG, "Wrong input. (checkpoint buffer size)");
+	WideCheckpointHeader hd;
+	const char *in = static_cast<const char *>(blob_host);
+	memcpy(&hd, in, sizeof(hd));
+	in += sizeof(hd);
+	if (hd.magic != WIDE_CHECKPOINT_MAGIC || hd.version != 1 || hd.n != Model::N || hd.B != h->B || hd.D != h->D || hd.npar != Model::NPAR)
+		return fail(JSDE_E_ARG, "Wrong input. (checkpoint belongs to a different model or ensemble shape)");
+	int rc = bind(h);
+	if (rc) return rc;
+	h->ctrl = hd.ctrl;
+	h->first_step = hd.first_step;
+	for (auto &s : checkpoint_sections(h)) {
+		CU(cudaMemcpyAsync(s.first, in, s.second, cudaMemcpyHostToDevice, h->stream));
+		in += s.second;
+	}
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
 
 int jsde_measure_fp64_peak(int device, double *tflops)
 {

@@ -79,6 +79,20 @@ def test_wide_sampling_grid_equals_repeated_calls(monkeypatch, tpb):
 	assert_bits_equal(E.get_state(), F.get_state(), "continued")
 
 
+def test_wide_checkpoint_restore():
+	spec = models.fhn_small
+	B = 11
+	E, _, _ = run(spec, B, 0.8)
+	blob = E.checkpoint()
+	E.integrate(2.0)
+	want = E.get_state()
+	F = Ensemble(spec, B)
+	F.restore(blob)
+	F.integrate(2.0)
+	assert_bits_equal(F.get_state(), want, "restored into a fresh handle")
+	assert_bits_equal(F.t, E.t, "times")
+
+
 def test_wide_failure_paths_and_unsupported_calls():
 	spec = models.fhn_small
 	E, stats, _ = run(spec, 4, 1.0, min_step=10.0, max_step=10.0, first_step=10.0)
