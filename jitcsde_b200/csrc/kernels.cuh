@@ -8,51 +8,9 @@
 
 namespace jsde {
 
-constexpr int BLOCK = 128;
-#ifndef JSDE_MIN_BLOCKS
-#define JSDE_MIN_BLOCKS 4  // resident blocks per SM the register allocator must leave room for
-#endif
+constexpr int BLOCK = 128;  // single-step kernels: one trajectory per thread
 
-// ---- totals: warp-reduce, one atomic per warp -------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
-{
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
-		v += __shfl_xor_sync(0xffffffffu, v, o);
-	return v;
-}
-
-__device__ __forceinline__ int warp_max(int v)
-{
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
-		v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-	return v;
-}
-
-__device__ __forceinline__ void add_totals(CallTotals *tot, unsigned long long acc, unsigned long long rej, unsigned long long fresh,
-	unsigned long long jumps, int min_step, int overflow, int depth)
-{
-	acc = warp_sum(acc);
-	rej = warp_sum(rej);
-	fresh = warp_sum(fresh);
-	jumps = warp_sum(jumps);
-	const unsigned long long ms = warp_sum((unsigned long long)min_step);
-	const unsigned long long ov = warp_sum((unsigned long long)overflow);
-	depth = warp_max(depth);
-	if ((threadIdx.x & 31) == 0) {
-		if (acc) atomicAdd(&tot->accepted, acc);
-		if (rej) atomicAdd(&tot->rejected, rej);
-		if (fresh) atomicAdd(&tot->fresh_draws, fresh);
-		if (jumps) atomicAdd(&tot->jumps, jumps);
-		if (ms) atomicAdd((unsigned long long *)&tot->n_min_step, ms);
-		if (ov) atomicAdd((unsigned long long *)&tot->n_overflow, ov);
-		if (depth) atomicMax(&tot->max_depth, depth);
-	}
-}
-
-// ---- the hot path -------------------------------------------------------------------------------------------------
-// Shared memory: one set of generator FIFOs per warp (warp_rng.cuh).
+// ---- shared memory of the single-step kernels: one set of generator FIFOs per warp (warp_rng.cuh) ---------------------
 constexpr int LOG_TAB_DOUBLES = 256;  // {invc, logc}[128], shared by the block
 
 template <class Model>
@@ -72,6 +30,7 @@ __device__ __forceinline__ WarpRng<Model::N> make_rng(const EnsembleView &e, int
 	return WarpRng<Model::N>(jsde_smem + LOG_TAB_DOUBLES + warp * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP, jsde_smem, e.mt, k - (threadIdx.x & 31), live);
 }
 
+// ---- the hot path -------------------------------------------------------------------------------------------------
 // jitcsde.integrate (_jitcsde.py:597-630) and, with a tape, jitcsde_jump.integrate (:693-700) for every trajectory.
 // Warp-specialised (duo.cuh): consumer warp w steps trajectories [128*block + 32*w, +32), one per lane, one attempted
 // step per round; producer warp w keeps their polar-pair FIFOs filled.  Choosing the next target and applying a jump

@@ -29,14 +29,13 @@ namespace jsde {
 constexpr int RNG_GROUP = 8;     // candidates per trajectory per op
 constexpr int RNG_STRIDE = 33;   // row stride (doubles) of the FIFO arrays: conflict-free column writes
 
-// 16-byte asynchronous copy global -> shared (LDGSTS): no register, no scoreboard wait until cp_async_wait_all()
+// 16-byte asynchronous copy global -> shared (LDGSTS): no register, no scoreboard wait until cp.async.wait_group
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
 	const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 constexpr int RNG_STAGE_CHUNKS = 18;   // staged words of one trajectory and slot (duo.cuh): chunks c..c+8 and c+99..c+107
 
