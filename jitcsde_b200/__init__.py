@@ -9,7 +9,7 @@ B200-native ensemble SDE integrator behind the JiTCSDE API (reference `jitcsde/_
 The CUDA library is compiled at run time with nvcc for sm_100a; there is no CPU fallback.
 """
 
-from ._jitcsde import UnsuccessfulIntegration, jitcsde, jitcsde_jump, t, test, xi, y  # noqa: F401
+from ._jitcsde import UnsuccessfulIntegration, jitcsde, jitcsde_jump, t, tau, test, xi, y  # noqa: F401
 from .modelspec import JumpSpec, ModelSpec  # noqa: F401
 
-__all__ = ["jitcsde", "jitcsde_jump", "y", "t", "xi", "UnsuccessfulIntegration", "test", "ModelSpec", "JumpSpec"]
+__all__ = ["jitcsde", "jitcsde_jump", "y", "t", "xi", "tau", "UnsuccessfulIntegration", "test", "ModelSpec", "JumpSpec"]

@@ -23,6 +23,8 @@ y = sympy.Function("y", real=True)
 t = sympy.Symbol("t", real=True)
 #: the per-jump standard-normal variate available to jump-amplitude expressions (see `JumpSpec`)
 xi = sympy.Symbol("xi", real=True)
+#: the tape's value for the jump being scheduled, available to waiting-time expressions (see `JumpSpec.iji`)
+tau = sympy.Symbol("tau", real=True)
 
 
 class _Printer(C99CodePrinter):
@@ -132,7 +134,7 @@ def stratonovich_to_ito(f, g):
 
 
 def spec_from_symbolic(f_sym, g_sym, *, n=None, additive=None, ito=True, control_pars=(), helpers=None, g_helpers="auto",
-		jump_amp=None, name=None, simplify=None) -> ModelSpec:
+		jump_amp=None, jump_iji=None, name=None, simplify=None) -> ModelSpec:
 	f = _handle_input(f_sym)
 	g = _handle_input(g_sym)
 	if n is None:
@@ -157,17 +159,17 @@ def spec_from_symbolic(f_sym, g_sym, *, n=None, additive=None, ito=True, control
 		g = [sympy.simplify(e) for e in g]
 	pars = tuple(str(p) for p in control_pars)
 	for p in pars:
-		if p in ("t", "h", "y", "Y", "out", "par", "xi") or not p.isidentifier():
+		if p in ("t", "h", "y", "Y", "out", "par", "xi", "tau") or not p.isidentifier():
 			raise ValueError(f"control parameter name {p!r} is not usable in generated code")
 	jump = None
 	if jump_amp is not None:
 		amp = [_to_sympy(e) for e in jump_amp]
 		if len(amp) != n:
 			raise ValueError("Output of amp function has the wrong dimension")
-		jump = JumpSpec(tuple(ccode(e) for e in amp))
+		jump = JumpSpec(tuple(ccode(e) for e in amp), iji="tau" if jump_iji is None else ccode(_to_sympy(jump_iji)))
 	fs = tuple(ccode(e) for e in f)
 	gs = tuple(ccode(e) for e in g)
 	if name is None:
 		import hashlib
-		name = "sde_" + hashlib.sha256("|".join((*fs, "#", *gs, "#", *pars, "#", *(jump.amp if jump else ()))).encode()).hexdigest()[:12]
+		name = "sde_" + hashlib.sha256("|".join((*fs, "#", *gs, "#", *pars, "#", *(jump.amp if jump else ()), "#", (jump.iji if jump else ""))).encode()).hexdigest()[:12]
 	return ModelSpec(name, n, bool(additive), fs, gs, control_pars=pars, jump=jump), f, g

@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _abi, _build
 from ._abi import ControllerParameters, Ensemble
-from ._codegen import check_expressions, spec_from_symbolic, t, xi, y  # noqa: F401  (re-exported)
+from ._codegen import check_expressions, spec_from_symbolic, t, tau, xi, y  # noqa: F401  (re-exported)
 from .modelspec import ModelSpec
 
 
@@ -53,7 +53,7 @@ class jitcsde:
 
 	def __init__(self, f_sym=(), g_sym=(), *, helpers=None, g_helpers="auto", n=None, additive=None, ito=True,
 			control_pars=(), callback_functions=(), verbose=True, module_location=None,
-			ensemble=1, device=0, noise_capacity=0, spec: ModelSpec | None = None, _jump_amp=None):
+			ensemble=1, device=0, noise_capacity=0, spec: ModelSpec | None = None, _jump_amp=None, _jump_iji=None):
 		if callback_functions:
 			raise NotImplementedError("Python callbacks cannot run inside a GPU kernel; express the term symbolically.")
 		if module_location is not None and spec is None:
@@ -72,7 +72,7 @@ class jitcsde:
 			if f_sym and not g_sym:
 				raise ValueError("You gave f_sym as an argument but not g_sym. JiTCSDE cannot properly work with this.")
 			self.spec, self.f_sym, self.g_sym = spec_from_symbolic(f_sym, g_sym, n=n, additive=additive, ito=ito,
-				control_pars=control_pars, helpers=helpers, g_helpers=g_helpers, jump_amp=_jump_amp)
+				control_pars=control_pars, helpers=helpers, g_helpers=g_helpers, jump_amp=_jump_amp, jump_iji=_jump_iji)
 		self.n = self.spec.n
 		self.additive = self.spec.additive
 		self.integration_parameters_set = False
@@ -97,7 +97,7 @@ class jitcsde:
 		if self.f_sym is None:
 			return
 		problems = check_expressions(self.f_sym, self.g_sym, self.n, self.control_pars,
-			extra_symbols=(xi,) if self.spec.jump else ())
+			extra_symbols=(xi, tau) if self.spec.jump else ())
 		if problems:
 			raise ValueError(problems[0] if fail_fast else "\n".join(problems))
 
@@ -353,15 +353,19 @@ class jitcsde_jump(jitcsde):
 	xis : optional array (L,) / (B, L) of variates; drawn from `rng.standard_normal` if omitted.
 	tape_length : L when IJI is a callable (default 1024).  Past the tape's end no further jumps happen
 		(`tape_exhausted` tells).
+	waiting_time : optional symbolic expression in `y(i)`, `t` and `tau` — the reference's state- and time-dependent
+		`IJI(time, state)` (`_jitcsde.py:682-687`), evaluated on the device when a jump is scheduled; `tau` is the
+		tape's value for that jump (e.g. unit exponentials from `IJI`, and `tau/rate(y)` here).  Default: `tau`.
 	"""
 
-	def __init__(self, IJI, amp, *args, rng=None, ito=True, xis=None, tape_length=1024, **kwargs):
+	def __init__(self, IJI, amp, *args, rng=None, ito=True, xis=None, tape_length=1024, waiting_time=None, **kwargs):
 		if not ito:
 			raise NotImplementedError("I don’t know how to convert jumpy Stratonovich SDEs to Itō SDEs – nobody does.")
 		if rng is None:
 			rng = np.random.default_rng()
 		if "spec" not in kwargs:
 			kwargs["_jump_amp"] = list(amp) if not callable(amp) else self._refuse_callable_amp()
+			kwargs["_jump_iji"] = waiting_time
 		super().__init__(*args, **kwargs)
 		if self.spec.jump is None:
 			raise ValueError("the model has no jump amplitude")

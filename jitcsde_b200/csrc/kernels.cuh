@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N>::BLOCKS) k_inte
 				to_jump = false;
 				if (Model::HAS_JUMP && use_tape) {
 					if (!jump_set) {  // next_jump property (:682-687): t + IJI(t, y)
-						const double wait = tape_pos < e.tape_len ? e.taus[(int64_t)k * e.tape_len + tape_pos] : __longlong_as_double(0x7ff0000000000000LL);
+						const double wait = tape_pos < e.tape_len ? Model::waiting_time(L.t, L.y, e.taus[(int64_t)k * e.tape_len + tape_pos], L.par)
+							: __longlong_as_double(0x7ff0000000000000LL);
 						next_jump = L.t + wait;
 						jump_set = true;
 					}

@@ -28,6 +28,13 @@ lorenz_jumpy = ModelSpec(
 	jump=JumpSpec(("0.0", "0.0", "0.0 + fabs(y(2))*xi")),
 )
 
+#: the same with a state-dependent jump intensity: the tape holds unit exponentials, the waiting time is E/(1 + y2^2/400)
+#: (reference `IJI(time, state)`, `_jitcsde.py:682-687`, evaluated when the jump is scheduled)
+lorenz_jumpy_rate = ModelSpec(
+	"lorenz_jumpy_rate", 3, False, _LORENZ_F, ("0.1*y(0)", "0.1*y(1)", "0.1*y(2)"),
+	jump=JumpSpec(("0.0", "0.0", "0.0 + fabs(y(2))*xi"), iji="tau/(1.0+y(2)*y(2)/400.0)+0.001*t"),
+)
+
 #: geometric Brownian motion, closed-form moments (SURVEY §8 d config 3 i)
 gbm = ModelSpec("gbm", 1, False, ("0.05*y(0)",), ("0.2*y(0)",))
 
@@ -101,6 +108,6 @@ def fhn_1000() -> ModelSpec:
 
 
 ALL = {m.name: m for m in (
-	lorenz_additive, lorenz_additive_fixture, lorenz_multiplicative, lorenz_jumpy,
+	lorenz_additive, lorenz_additive_fixture, lorenz_multiplicative, lorenz_jumpy, lorenz_jumpy_rate,
 	gbm, gbm_pars, duffing, ou, ou_timedep, cubic, ring6, ring6_mult, fhn_small,
 )}

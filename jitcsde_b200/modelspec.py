@@ -27,8 +27,14 @@ class JumpSpec:
 	(reference `jitcsde/_jitcsde.py:656-700`).  Waiting times and one standard-normal variate per jump come from a
 	per-trajectory *tape*; ``amp`` holds one C expression per component in ``y(i)``, ``t`` and ``xi`` (the tape's
 	variate for this jump).  The expression is evaluated on the *pre-jump* state, like `_jitcsde.py:697`.
+
+	``iji`` is the reference's ``IJI(time, state)`` (`_jitcsde.py:682-687`: evaluated when the next jump is scheduled, on
+	the state right after the previous one): a C expression in ``y(i)``, ``t`` and ``tau``, the tape's value for this
+	jump.  The default ``"tau"`` makes the tape hold the waiting times themselves; ``"tau/(1.0+y(2)*y(2))"`` with unit
+	exponentials on the tape gives a state-dependent intensity (SURVEY.md §8 f item 3).
 	"""
 	amp: tuple[str, ...]
+	iji: str = "tau"
 
 
 @dataclass(frozen=True)
@@ -94,7 +100,7 @@ JSDE_MODEL_FN double jsde_coupling_sum(int i, const double *Y)
 	def digest(self) -> str:
 		h = hashlib.sha256()
 		for part in (self.name, str(self.n), str(self.additive), *self.f, "|", *self.g, "|", *self.control_pars,
-				"|", *(self.jump.amp if self.jump else ()), "|", self.preamble, self.f_body, self.g_body, self.f_component, self.g_component,
+				"|", *(self.jump.amp if self.jump else ()), "|", (self.jump.iji if self.jump and self.jump.iji != "tau" else ""), "|", self.preamble, self.f_body, self.g_body, self.f_component, self.g_component,
 				str(self.coupling_units), self.coupling_table):
 			h.update(part.encode())
 			h.update(b"\0")

@@ -115,18 +115,21 @@ class RefJumpIntegrator(RefIntegrator):
 		return super().integrate(target_time)
 
 
-def tape_closures(taus, xis, amp_fn):
+def tape_closures(taus, xis, amp_fn, iji_fn=None):
 	"""
 	Feed a per-trajectory jump tape (waiting times `taus`, standard-normal variates `xis`) to the reference's
 	callback interface: the k-th call of IJI returns taus[k]; the k-th call of amp evaluates `amp_fn(t, y, xis[k])`.
-	Past the end of the tape the waiting time is +inf (no further jumps).
+	Past the end of the tape the waiting time is +inf (no further jumps).  `iji_fn(t, y, tau)` turns the tape's value into
+	the waiting time (default: the value itself) — the state-dependent intensities of `JumpSpec.iji`.
 	"""
 	state = {"i": 0, "j": 0}
 
 	def IJI(time, y):
 		k = state["i"]
 		state["i"] += 1
-		return float(taus[k]) if k < len(taus) else float("inf")
+		if k >= len(taus):
+			return float("inf")
+		return float(taus[k]) if iji_fn is None else float(iji_fn(time, y, float(taus[k])))
 
 	def amp(time, y):
 		k = state["j"]

@@ -96,3 +96,14 @@ def test_generated_model_compiles():
 	S = jitcsde(f, g, verbose=False)
 	assert S.compile_C().endswith(".so")
 	assert issubclass(UnsuccessfulIntegration, Exception)
+
+
+def test_jump_waiting_time_expression_is_printed_into_the_spec():
+	from jitcsde_b200 import jitcsde_jump, tau
+	f = [10 * (y(1) - y(0)), y(0) * (28 - y(2)) - y(1), y(0) * y(1) - 8 / 3 * y(2)]
+	g = [0.1 * y(i) for i in range(3)]
+	SDE = jitcsde_jump(np.ones(4), [0, 0, abs(y(2)) * xi], f, g, waiting_time=tau / (1 + y(2) ** 2), verbose=False)
+	assert SDE.spec.jump.iji.replace(" ", "") == "tau/(((y(2))*(y(2)))+1)"
+	SDE.check()
+	plain = jitcsde_jump(np.ones(4), [0, 0, abs(y(2)) * xi], f, g, verbose=False)
+	assert plain.spec.jump.iji == "tau" and plain.spec.name != SDE.spec.name

@@ -392,6 +392,24 @@ def test_jumps_vs_oracle_many():
 		assert_bits_equal(y[k], P.get_state(), f"trajectory {k}")
 
 
+def test_state_dependent_jump_intensity_vs_oracle():
+	"""JumpSpec.iji (the reference's IJI(time, state)): waiting times computed on the device from the tape's unit
+	exponentials and the state at scheduling time."""
+	spec = models.lorenz_jumpy_rate
+	B = 200
+	E, y0, seeds = make(spec, B)
+	taus, xis = jump_tape(B, 24)
+	st = E.integrate_jumps(1.5, taus, xis)
+	E.integrate_jumps(3.0, taus, xis)
+	assert st["jumps"] > B // 2
+	y = E.get_state()
+	for k in range(0, B, 9):
+		P = port.PortCore(spec, y0[k], 0.0, int(seeds[k]))
+		P.integrate_jumps(1.5, taus[k], xis[k])
+		P.integrate_jumps(3.0, taus[k], xis[k])
+		assert_bits_equal(y[k], P.get_state(), f"trajectory {k}")
+
+
 def test_control_parameters():
 	B = 64
 	E, y0, seeds = make(models.gbm_pars, B)

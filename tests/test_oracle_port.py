@@ -144,6 +144,30 @@ def test_against_live_reference_core(name):
 		assert P.dt == R.dt
 
 
+def test_state_dependent_jump_intensity_against_live_reference_core():
+	"""JumpSpec.iji: the port's compiled waiting-time expression == the same law fed to the reference's IJI(time, state)
+	callback (`_jitcsde.py:682-700`), bit for bit."""
+	spec = models.lorenz_jumpy_rate
+	base = models.lorenz_jumpy  # same SDE: the reference core has no notion of jumps, its Python driver has
+	if not build_ref.available(base, "strict"):
+		pytest.skip("reference core neither buildable nor prebuilt here")
+	mod = build_ref.load(base, "strict")
+	y0, seeds = ensemble_inputs(spec.n, 3)
+	taus, xis = jump_tape(3, 24)
+	for k in range(3):
+		IJI, amp = ref_driver.tape_closures(taus[k], xis[k], lambda t, y, xi: np.array([0.0, 0.0, 0.0 + abs(y[2]) * xi]),
+			iji_fn=lambda t, y, tau: tau / (1.0 + y[2] * y[2] / 400.0) + 0.001 * t)
+		R = ref_driver.RefJumpIntegrator(IJI, amp, mod, y0[k], 0.0, int(seeds[k]))
+		R.integrate(2.0)
+		yr = R.integrate(4.0)
+		P = port.PortCore(spec, y0[k], 0.0, int(seeds[k]))
+		P.integrate_jumps(2.0, taus[k], xis[k])
+		P.integrate_jumps(4.0, taus[k], xis[k])
+		assert_bits_equal(P.get_state(), yr, f"trajectory {k}")
+		c = P.counters()
+		assert (c["accepted"], c["rejected"]) == (R.accepted, R.rejected)
+
+
 # ---- noise-memory invariants (reference tests/test_python_core.py:31-61, restated for the port's queue) -------
 def test_noise_memory_invariants():
 	spec = models.ModelSpec("unit_noise2", 1, True, ("0.0",), ("1.0",))
