@@ -15,9 +15,10 @@ for r in rows:
 	if cur == 'duo.cuh' and 'PairConsumer' in ''.join(r[1:2]): role = 'consumer'
 	if cur == 'duo.cuh' and 70 <= line <= 105: role = 'consumer'
 	for h, v in zip(hdr, r):
-		if h.startswith('stall_') and 'Not Issued' not in h:
+		if h.startswith('stall_') and 'Not Issued' not in h and v.isdigit():
 			role_stall[role][h] += int(v)
-	inst[role] += int(r[hdr.index("Instructions Executed")])
+	executed = r[hdr.index("Instructions Executed")]
+	inst[role] += int(executed) if executed.isdigit() else 0
 for role in role_stall:
 	tot = sum(role_stall[role].values())
 	print(role, 'inst', inst[role], 'samples', tot)
