@@ -55,7 +55,7 @@ ABI_SYMBOLS = (
 	"jsde_set_integration_parameters", "jsde_set_parameters", "jsde_pin_noise", "jsde_integrate", "jsde_integrate_jumps", "jsde_integrate_grid",
 	"jsde_get_state", "jsde_get_controller_state", "jsde_moments", "jsde_get_next_step", "jsde_get_p", "jsde_accept_step",
 	"jsde_apply_jump", "jsde_set_time", "jsde_draw_gauss_debug", "jsde_dump_noise", "jsde_measure_fp64_peak",
-	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_shared_div", "jsde_debug_inline_math", "jsde_checkpoint_bytes", "jsde_checkpoint_save", "jsde_checkpoint_restore", "jsde_last_error", "jsde_version",
+	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_shared_div", "jsde_debug_inline_math", "jsde_pin_noise_path", "jsde_checkpoint_bytes", "jsde_checkpoint_save", "jsde_checkpoint_restore", "jsde_last_error", "jsde_version",
 )
 
 
@@ -198,6 +198,21 @@ class Ensemble:
 
 	def pin_noise(self, number, step):
 		self._check(self.lib.jsde_pin_noise(self._h, int(number), float(step)))
+
+	def pin_noise_path(self, steps, dw, dz):
+		"""Append caller-supplied Wiener increments to the noise memory: steps [K], dw and dz [B][K][n] (or [K][n],
+		broadcast).  Integration then runs along this path for sum(steps) time units (Brownian bridges in between)."""
+		steps = np.ascontiguousarray(steps, dtype=np.float64)
+		dw = np.asarray(dw, dtype=np.float64)
+		dz = np.asarray(dz, dtype=np.float64)
+		if dw.ndim == 2:
+			dw = np.broadcast_to(dw, (self.B,) + dw.shape)
+			dz = np.broadcast_to(dz, (self.B,) + dz.shape)
+		if dw.shape != (self.B, steps.size, self.n) or dz.shape != dw.shape:
+			raise ValueError("dw and dz must have shape [B][len(steps)][n]")
+		dw, dz = np.ascontiguousarray(dw), np.ascontiguousarray(dz)
+		self.lib.jsde_pin_noise_path.argtypes = [ctypes.c_void_p, ctypes.c_uint, c_double_p, c_double_p, c_double_p]
+		self._check(self.lib.jsde_pin_noise_path(self._h, steps.size, _dp(steps), _dp(dw), _dp(dz)))
 
 	# ---- the hot path ---------------------------------------------------------------------------------------------------
 	def integrate(self, target_time) -> dict:

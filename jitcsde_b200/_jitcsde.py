@@ -310,6 +310,12 @@ class jitcsde:
 			warn("`number` does not appear to be a integer. This is very likely cause an error immediately.", stacklevel=2)
 		self.SDE.pin_noise(number, step_size)
 
+	def pin_noise_path(self, steps, dw, dz):
+		"""Pre-fill the noise memory with caller-supplied Wiener increments (steps [K]; dw, dz [B][K][n] or [K][n]) instead
+		of fresh draws: integrate along a prescribed Brownian path (no counterpart in the reference)."""
+		self._initiate()
+		self.SDE.pin_noise_path(steps, dw, dz)
+
 	def checkpoint(self):
 		"""The whole integrator state (states, times, step sizes, noise memory, every trajectory's generator state,
 		counters, jump scheduling, controller) as a uint8 array — for long campaigns (SURVEY.md §8 f item 4; the reference

@@ -348,6 +348,38 @@ int jsde_pin_noise(jsde_t *h, unsigned number, double step)
 	return JSDE_OK;
 }
 
+int jsde_pin_noise_path(jsde_t *h, unsigned number, const double *steps_host, const double *dw_host, const double *dz_host)
+{
+	if (!h || (number && (!steps_host || !dw_host || !dz_host)))
+		return fail(JSDE_E_ARG, "Wrong input.");
+	for (unsigned j = 0; j < number; j++)
+		if (!(steps_host[j] > 0.0))
+			return fail(JSDE_E_ARG, "Wrong input. (step sizes must be positive)");
+	if (number == 0)
+		return JSDE_OK;
+	int rc = bind(h);
+	if (rc) return rc;
+	const size_t values = (size_t)h->B * number * Model::N;
+	double *steps = nullptr, *dw = nullptr, *dz = nullptr;
+	cudaError_t err = cudaMalloc(&steps, number * sizeof(double));
+	if (err == cudaSuccess) err = cudaMalloc(&dw, values * sizeof(double));
+	if (err == cudaSuccess) err = cudaMalloc(&dz, values * sizeof(double));
+	auto cleanup = [&]() { cudaFree(steps); cudaFree(dw); cudaFree(dz); };
+	if (err != cudaSuccess) { cleanup(); return fail(JSDE_E_NOMEM, cudaGetErrorString(err)); }
+	err = cudaMemcpyAsync(steps, steps_host, number * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+	if (err == cudaSuccess) err = cudaMemcpyAsync(dw, dw_host, values * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+	if (err == cudaSuccess) err = cudaMemcpyAsync(dz, dz_host, values * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+	if (err == cudaSuccess) {
+		k_pin_path<Model><<<grid_for(h->B, BLOCK), BLOCK, 0, h->stream>>>(h->v, number, steps, dw, dz);
+		err = cudaGetLastError();
+	}
+	if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
+	cleanup();
+	if (err != cudaSuccess)
+		return fail(JSDE_E_CUDA, cudaGetErrorString(err));
+	return JSDE_OK;
+}
+
 static int integrate_common(jsde_t *h, double target_time, int use_tape, jsde_stats *stats_host,
 	const double *grid_times_dev = nullptr, int grid_count = 0, double *grid_out_dev = nullptr)
 {

@@ -321,6 +321,30 @@ __global__ void __launch_bounds__(BLOCK) k_pin_noise(EnsembleView e, unsigned nu
 	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 }
 
+// pin_noise with caller-supplied Wiener increments: item j of trajectory k has length steps[j], DW = dw[k][j][·],
+// DZ = dz[k][j][·] (no generator involved)
+template <class Model>
+__global__ void __launch_bounds__(BLOCK) k_pin_path(EnsembleView e, unsigned number, const double *steps, const double *dw, const double *dz)
+{
+	constexpr int N = Model::N;
+	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+	if (k >= e.B)
+		return;
+	WarpRng<N> rng(nullptr, nullptr, e.mt, 0, false);
+	Lane<Model> L(e, k, rng);
+	L.load();
+	for (unsigned j = 0; j < number && L.status == TRAJ_OK; j++) {
+		double W[N], Z[N];
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			W[i] = dw[((int64_t)k * number + j) * N + i];
+			Z[i] = dz[((int64_t)k * number + j) * N + i];
+		}
+		L.pin_given(steps[j], W, Z);
+	}
+	L.store();
+}
+
 // rk_gauss stream of every trajectory: out [B][pairs][2]
 template <class Model>
 __global__ void __launch_bounds__(BLOCK) k_draw_gauss(EnsembleView e, double scale, int pairs, double *out)

@@ -323,6 +323,19 @@ struct Lane {
 		max_depth = count > max_depth ? count : max_depth;
 	}
 
+	// the same with caller-supplied increments instead of a fresh draw (jsde_pin_noise_path)
+	__device__ __forceinline__ void pin_given(double step, const double (&W)[N], const double (&Z)[N])
+	{
+		if (count >= e.D) {
+			status = TRAJ_NOISE_OVERFLOW;
+			return;
+		}
+		store_item(count, step, W, Z);
+		count++;
+		cursor = count - 1;
+		max_depth = count > max_depth ? count : max_depth;
+	}
+
 	// ---- proposal (get_next_step) ---------------------------------------------------------------------------------
 	__device__ __forceinline__ bool propose(double h)
 	{

@@ -442,6 +442,32 @@ def test_pin_noise_and_dump():
 		assert_bits_equal(E.dump_noise(k), P.dump_queue(), f"noise memory {k}")
 
 
+def test_pin_noise_path_vs_oracle():
+	"""Caller-supplied Wiener path: same noise memory as the oracle, same integration along it (whole items, Brownian
+	bridges inside items, fresh noise beyond the path's end)."""
+	spec = models.lorenz_multiplicative
+	B, K = 40, 12
+	rng = np.random.default_rng(5)
+	steps = rng.uniform(2e-3, 2e-2, K)
+	dw = rng.standard_normal((B, K, spec.n)) * np.sqrt(steps)[None, :, None]
+	dz = rng.standard_normal((B, K, spec.n)) * np.sqrt(steps)[None, :, None]
+	E, y0, seeds = make(spec, B)
+	E.pin_noise_path(steps, dw, dz)
+	got = E.dump_noise(7)
+	assert got.shape == (K, 1 + 2 * spec.n)
+	assert_bits_equal(got[:, 0], steps, "item lengths")
+	assert_bits_equal(got[:, 1:1 + spec.n], dw[7], "DW")
+	T = float(steps.sum() * 1.5)  # half of the run uses fresh noise
+	E.integrate(T)
+	y = E.get_state()
+	for k in range(0, B, 3):
+		P = port.PortCore(spec, y0[k], 0.0, int(seeds[k]))
+		P.pin_path(steps, dw[k], dz[k])
+		assert_bits_equal(y[k], P.integrate(T), f"trajectory {k}")
+	with pytest.raises(JsdeError, match="positive"):
+		E.pin_noise_path([0.0], np.zeros((B, 1, spec.n)), np.zeros((B, 1, spec.n)))
+
+
 def test_unsuccessful_integration_status():
 	"""reference tests/test_jitcsde.py:221-240: min_step=10 cannot be met"""
 	spec = models.lorenz_multiplicative

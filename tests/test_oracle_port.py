@@ -168,6 +168,28 @@ def test_state_dependent_jump_intensity_against_live_reference_core():
 		assert (c["accepted"], c["rejected"]) == (R.accepted, R.rejected)
 
 
+def test_pinned_path_is_consumed_exactly():
+	"""port.pin_path (the checker of jsde_pin_noise_path): steps that coincide with the pinned items consume them whole,
+	so a noise-driven-only SDE (f = 0, g = 1) reproduces the path's partial sums exactly."""
+	spec = models.ModelSpec("unit_noise3", 1, True, ("0.0",), ("1.0",))
+	rng = np.random.default_rng(3)
+	steps = rng.uniform(0.01, 0.1, 6)
+	dw = rng.standard_normal((6, 1)) * np.sqrt(steps)[:, None]
+	dz = rng.standard_normal((6, 1)) * np.sqrt(steps)[:, None]
+	P = port.PortCore(spec, [0.0], 0.0, 1)
+	P.pin_path(steps, dw, dz)
+	q = P.dump_queue()
+	assert_bits_equal(q[:, 0], steps, "lengths")
+	assert_bits_equal(q[:, 1], dw[:, 0], "DW")
+	total = 0.0
+	for j, h in enumerate(steps):
+		P.get_next_step(float(h))
+		P.accept_step()
+		total = total + dw[j, 0]
+		assert P.get_state()[0] == total
+	assert len(P.dump_queue()) == 0
+
+
 # ---- noise-memory invariants (reference tests/test_python_core.py:31-61, restated for the port's queue) -------
 def test_noise_memory_invariants():
 	spec = models.ModelSpec("unit_noise2", 1, True, ("0.0",), ("1.0",))
