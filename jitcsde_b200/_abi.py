@@ -55,7 +55,7 @@ ABI_SYMBOLS = (
 	"jsde_set_integration_parameters", "jsde_set_parameters", "jsde_pin_noise", "jsde_integrate", "jsde_integrate_jumps", "jsde_integrate_grid",
 	"jsde_get_state", "jsde_get_controller_state", "jsde_moments", "jsde_get_next_step", "jsde_get_p", "jsde_accept_step",
 	"jsde_apply_jump", "jsde_set_time", "jsde_draw_gauss_debug", "jsde_dump_noise", "jsde_measure_fp64_peak",
-	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_shared_div", "jsde_debug_inline_math", "jsde_pin_noise_path", "jsde_checkpoint_bytes", "jsde_checkpoint_save", "jsde_checkpoint_restore", "jsde_last_error", "jsde_version",
+	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_shared_div", "jsde_debug_inline_math", "jsde_pin_noise_path", "jsde_integrate_jumps_generated", "jsde_generated_jump_tape", "jsde_checkpoint_bytes", "jsde_checkpoint_save", "jsde_checkpoint_restore", "jsde_last_error", "jsde_version",
 )
 
 
@@ -232,6 +232,14 @@ class Ensemble:
 		self.last_stats = st.as_dict()
 		return self.last_stats
 
+	def integrate_jumps_generated(self, target_time, seed, first_index=0) -> dict:
+		"""Jumps whose variates are generated on the device (counter-based, csrc/philox_jumps.h): no tape."""
+		st = Stats()
+		self.lib.jsde_integrate_jumps_generated.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_uint64, ctypes.c_int64, ctypes.c_void_p]
+		self._check(self.lib.jsde_integrate_jumps_generated(self._h, float(target_time), int(seed), int(first_index), ctypes.byref(st)))
+		self.last_stats = st.as_dict()
+		return self.last_stats
+
 	def integrate_grid(self, times, taus=None, xis=None):
 		"""States at every sample time, [n_times][B][n], from ONE launch (semantics of consecutive integrate() calls)."""
 		times = np.ascontiguousarray(times, dtype=np.float64)
@@ -376,3 +384,13 @@ def device_inline_math(lib, a, b, device=0):
 	if lib.jsde_debug_inline_math(device, _dp(a), _dp(b), _dp(div), okd.ctypes.data_as(c_u8_p), _dp(root), oks.ctypes.data_as(c_u8_p), a.size) != 0:
 		raise JsdeError(lib.jsde_last_error().decode())
 	return div, okd.astype(bool), root, oks.astype(bool)
+
+
+def generated_jump_tape(lib, seed, first_index, count, length, device=0):
+	"""(taus, xis), each [count][length]: the counter-based jump variates `integrate_jumps_generated` uses"""
+	taus = np.empty((count, length))
+	xis = np.empty((count, length))
+	lib.jsde_generated_jump_tape.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_double_p, c_double_p]
+	if lib.jsde_generated_jump_tape(device, int(seed), int(first_index), int(count), int(length), _dp(taus), _dp(xis)) != 0:
+		raise JsdeError(lib.jsde_last_error().decode())
+	return taus, xis

@@ -351,7 +351,8 @@ class jitcsde_jump(jitcsde):
 	`jitcsde` with random jumps (reference `_jitcsde.py:656-722`).  The reference takes two Python callables; a GPU lane
 	cannot call Python, so both are given declaratively and consumed from a per-trajectory *tape*:
 
-	IJI : waiting times.  Either an array of shape (L,) / (B, L) — the k-th jump of a trajectory happens that long
+	IJI : waiting times.  The string "generated" (unit exponentials drawn on the device by a counter-based generator —
+		no tape, no length limit; combine with `waiting_time` for a rate), or an array of shape (L,) / (B, L) — the k-th jump of a trajectory happens that long
 		after the previous one — or a callable `IJI(time, state)` that does not depend on its arguments (like the
 		reference's example, `examples/noisy_and_jumpy_lorenz.py:48-49`); it is called L times per trajectory up front.
 	amp : iterable of n symbolic expressions in `y(i)`, `t` and `xi`, where `xi` is the tape's standard-normal variate
@@ -376,10 +377,16 @@ class jitcsde_jump(jitcsde):
 		if self.spec.jump is None:
 			raise ValueError("the model has no jump amplitude")
 		self.rng = rng
-		self.IJI = IJI
+		self.IJI = IJI  # array, callable, or the string "generated" (device-side counter-based variates, see integrate)
+		self._first_index = 0  # global index of trajectory 0 (set it on every rank of a sharded ensemble)
 		self._xis_arg = xis
 		self._tape_length = tape_length
 		self._taus = self._xis = None
+
+	def _generated_seed(self):
+		if getattr(self, "_jump_seed", None) is None:
+			self._jump_seed = int(self.rng.integers(0, 2 ** 63))
+		return self._jump_seed
 
 	@staticmethod
 	def _refuse_callable_amp():
@@ -416,6 +423,12 @@ class jitcsde_jump(jitcsde):
 	def integrate(self, target_time):
 		"""reference `_jitcsde.py:693-700`, all trajectories in one launch"""
 		self._initiate()
+		if isinstance(self.IJI, str) and self.IJI == "generated":
+			# variates generated on the device (counter-based): unit exponentials feed `waiting_time`, no tape
+			stats = self.SDE.integrate_jumps_generated(target_time, self._generated_seed(), self._first_index)
+			self.last_stats = stats
+			self._raise_on_failure(stats)
+			return self._shape_out(self.SDE.get_state())
 		self._make_tape()
 		stats = self.SDE.integrate_jumps(target_time, self._taus, self._xis)
 		self.last_stats = stats

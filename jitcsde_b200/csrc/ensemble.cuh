@@ -63,6 +63,10 @@ struct EnsembleView {
 	long long *tape_pos;
 	const double *taus, *xis;
 	long long tape_len;
+	// counter-based jump variates instead of a tape (philox_jumps.h): generated where they are needed
+	int generated_jumps;
+	unsigned long long jump_seed;
+	long long jump_first;  // global index of trajectory 0 (sharded ensembles draw the same variates as one big one)
 	CallTotals *totals;
 };
 

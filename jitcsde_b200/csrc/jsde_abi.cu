@@ -200,6 +200,9 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	v.par_stride = 0;
 	v.taus = v.xis = nullptr;
 	v.tape_len = 0;
+	v.generated_jumps = 0;
+	v.jump_seed = 0;
+	v.jump_first = 0;
 	default_controller(h);
 	if ((err = cudaMemsetAsync(h->seeds, 0, B * sizeof(uint32_t), h->stream)) != cudaSuccess ||
 		(err = cudaMemsetAsync(v.y, 0, (size_t)B * n * sizeof(double), h->stream)) != cudaSuccess ||
@@ -496,7 +499,45 @@ int jsde_integrate_jumps(jsde_t *h, double target_time, const jsde_jump_tape *ta
 		h->v.xis = h->xis;
 		h->v.tape_len = tape->length;
 	}
+	h->v.generated_jumps = 0;
 	return integrate_common(h, target_time, 1, stats_host);
+}
+
+int jsde_integrate_jumps_generated(jsde_t *h, double target_time, uint64_t seed, int64_t first_index, jsde_stats *stats_host)
+{
+	if (!h || first_index < 0)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	if (!Model::HAS_JUMP)
+		return fail(JSDE_E_STATE, "this model was generated without a jump amplitude");
+	int rc = bind(h);
+	if (rc) return rc;
+	h->v.generated_jumps = 1;
+	h->v.jump_seed = seed;
+	h->v.jump_first = first_index;
+	return integrate_common(h, target_time, 1, stats_host);
+}
+
+int jsde_generated_jump_tape(int device, uint64_t seed, int64_t first_index, int64_t count, int64_t length, double *taus_host, double *xis_host)
+{
+	if (first_index < 0 || count < 0 || length < 0 || !taus_host || !xis_host)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	if (count * length == 0)
+		return JSDE_OK;
+	CU(cudaSetDevice(device));
+	const size_t bytes = (size_t)count * (size_t)length * sizeof(double);
+	double *taus = nullptr, *xis = nullptr;
+	cudaError_t err = cudaMalloc(&taus, bytes);
+	if (err == cudaSuccess) err = cudaMalloc(&xis, bytes);
+	if (err == cudaSuccess) {
+		k_jump_tape<<<grid_for(count * length, 256), 256>>>(seed, first_index, count, length, taus, xis);
+		err = cudaGetLastError();
+	}
+	if (err == cudaSuccess) err = cudaMemcpy(taus_host, taus, bytes, cudaMemcpyDeviceToHost);
+	if (err == cudaSuccess) err = cudaMemcpy(xis_host, xis, bytes, cudaMemcpyDeviceToHost);
+	cudaFree(taus); cudaFree(xis);
+	if (err != cudaSuccess)
+		return fail(JSDE_E_CUDA, cudaGetErrorString(err));
+	return JSDE_OK;
 }
 
 int jsde_get_state(jsde_t *h, double *y_host, double *t_host, int32_t *status_host)

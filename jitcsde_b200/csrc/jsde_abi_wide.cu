@@ -420,6 +420,8 @@ int jsde_set_time(jsde_t *h, const double *t_host)
 int jsde_pin_noise(jsde_t *, unsigned, double) { return unsupported("pin_noise"); }
 int jsde_pin_noise_path(jsde_t *, unsigned, const double *, const double *, const double *) { return unsupported("pin_noise_path"); }
 int jsde_integrate_jumps(jsde_t *, double, const jsde_jump_tape *, jsde_stats *) { return unsupported("jumps"); }
+int jsde_integrate_jumps_generated(jsde_t *, double, uint64_t, int64_t, jsde_stats *) { return unsupported("jumps"); }
+int jsde_generated_jump_tape(int, uint64_t, int64_t, int64_t, int64_t, double *, double *) { return unsupported("jumps"); }
 int jsde_get_next_step(jsde_t *, const double *) { return unsupported("the single-step surface"); }
 int jsde_get_p(jsde_t *, double, double, double *) { return unsupported("the single-step surface"); }
 int jsde_accept_step(jsde_t *, const uint8_t *) { return unsupported("the single-step surface"); }

@@ -5,6 +5,7 @@
 #include "stepper.cuh"
 #include "duo.cuh"
 #include "kernels_common.cuh"
+#include "philox_jumps.h"
 
 namespace jsde {
 
@@ -154,8 +155,11 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N>::BLOCKS) k_inte
 				to_jump = false;
 				if (Model::HAS_JUMP && use_tape) {
 					if (!jump_set) {  // next_jump property (:682-687): t + IJI(t, y)
-						const double wait = tape_pos < e.tape_len ? Model::waiting_time(L.t, L.y, e.taus[(int64_t)k * e.tape_len + tape_pos], L.par)
-							: __longlong_as_double(0x7ff0000000000000LL);
+						double wait = __longlong_as_double(0x7ff0000000000000LL);  // past the end of a tape: no further jumps
+						if (e.generated_jumps)
+							wait = Model::waiting_time(L.t, L.y, jsde_jump_tau(e.jump_seed, e.jump_first + k, tape_pos), L.par);
+						else if (tape_pos < e.tape_len)
+							wait = Model::waiting_time(L.t, L.y, e.taus[(int64_t)k * e.tape_len + tape_pos], L.par);
 						next_jump = L.t + wait;
 						jump_set = true;
 					}
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N>::BLOCKS) k_inte
 						}
 					} else {
 						double change[N];
-						Model::jump(L.t, L.y, e.xis[(int64_t)k * e.tape_len + tape_pos], L.par, change);
+						Model::jump(L.t, L.y, e.generated_jumps ? jsde_jump_xi(e.jump_seed, e.jump_first + k, tape_pos) : e.xis[(int64_t)k * e.tape_len + tape_pos], L.par, change);
 #pragma unroll
 						for (int i = 0; i < N; i++)
 							L.y[i] += change[i];
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N>::BLOCKS) k_inte
 							}
 						} else {
 							double change[N];  // apply_jump(amp(time, state)) (:696-698)
-							Model::jump(L.t, L.y, e.xis[(int64_t)k * e.tape_len + tape_pos], L.par, change);
+							Model::jump(L.t, L.y, e.generated_jumps ? jsde_jump_xi(e.jump_seed, e.jump_first + k, tape_pos) : e.xis[(int64_t)k * e.tape_len + tape_pos], L.par, change);
 #pragma unroll
 							for (int i = 0; i < N; i++)
 								L.y[i] += change[i];
@@ -343,6 +347,17 @@ __global__ void __launch_bounds__(BLOCK) k_pin_path(EnsembleView e, unsigned num
 		L.pin_given(steps[j], W, Z);
 	}
 	L.store();
+}
+
+// the counter-based jump variates as a tape: taus, xis [count][length] for trajectories first .. first+count-1
+__global__ void k_jump_tape(unsigned long long seed, long long first, long long count, long long length, double *taus, double *xis)
+{
+	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= count * length)
+		return;
+	const long long k = idx / length, j = idx - k * length;
+	taus[idx] = jsde_jump_tau(seed, first + k, j);
+	xis[idx] = jsde_jump_xi(seed, first + k, j);
 }
 
 // rk_gauss stream of every trajectory: out [B][pairs][2]
