@@ -128,3 +128,22 @@ def test_callable_waiting_times():
 	SDE.set_initial_value([1.0], 0.0)
 	out = SDE.integrate(2.0)
 	assert out.shape == (64, 1) and np.isfinite(out).all() and SDE.last_stats["jumps"] > 64
+
+
+def test_generated_jumps_with_a_rate_through_the_public_api():
+	"""jitcsde_jump(IJI="generated", waiting_time=tau/rate): no tape; deterministic given the rng that seeds the jump
+	generator; the jump count follows the rate."""
+	from jitcsde_b200 import tau
+
+	def run(seed):
+		SDE = jitcsde_jump("generated", [0.5 * xi], [-y(0)], [0.1], waiting_time=tau / 4.0, rng=np.random.default_rng(seed), ensemble=256, verbose=False)
+		SDE.set_seed(7)
+		SDE.set_initial_value(np.zeros(1), 0.0)
+		out = SDE.integrate(5.0)
+		return out, SDE.last_stats["jumps"]
+	a, ja = run(3)
+	b, jb = run(3)
+	c, _ = run(4)
+	assert_bits_equal(a, b, "same jump seed")
+	assert not np.array_equal(a, c)
+	assert ja == jb and abs(ja - 256 * 5.0 * 4.0) < 5 * np.sqrt(256 * 5.0 * 4.0)  # Poisson(rate 4 per unit time)
