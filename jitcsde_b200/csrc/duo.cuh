@@ -44,9 +44,11 @@ constexpr int DUO_PAIRS = 4;
 constexpr int DUO_BLOCK = 64 * DUO_PAIRS;
 // Resident blocks per SM and the register split between the warpgroups (the launch allocation 65536/(256*blocks),
 // rounded down to a multiple of 8, is redistributed by setmaxnreg: consumer + producer = 2 x allocation).  Up to three
-// components the stepper fits 104 registers and three blocks are resident; beyond that it would spill, so two blocks
-// with 168/88.  (Measured for n = 3: 112/48 and the two-block splits are 5-8 % slower.)  The macros override.
-template <int N>
+// components the stepper fits 104 registers (SRA) and three blocks are resident; beyond that it would spill, so two
+// blocks with 168/88.  The SRI stepper is 2.4 times the generator's work, so its producers wait most of the time and
+// can live with spills: 112/48 (SRI-Lorenz +11 %, Duffing +1.5 %); for SRA, where both roles are equally loaded, 112/48
+// and the two-block splits are 5-8 % slower.  The macros override.
+template <int N, bool ADDITIVE>
 struct DuoConfig {
 #ifdef JSDE_DUO_MIN_BLOCKS
 	static constexpr int BLOCKS = JSDE_DUO_MIN_BLOCKS;
@@ -56,12 +58,12 @@ struct DuoConfig {
 #ifdef JSDE_DUO_CONSUMER_REGS
 	static constexpr int CONSUMER_REGS = JSDE_DUO_CONSUMER_REGS;
 #else
-	static constexpr int CONSUMER_REGS = N <= 3 ? 104 : 168;
+	static constexpr int CONSUMER_REGS = N <= 3 ? (ADDITIVE ? 104 : 112) : 168;
 #endif
 #ifdef JSDE_DUO_PRODUCER_REGS
 	static constexpr int PRODUCER_REGS = JSDE_DUO_PRODUCER_REGS;
 #else
-	static constexpr int PRODUCER_REGS = N <= 3 ? 56 : 88;
+	static constexpr int PRODUCER_REGS = N <= 3 ? (ADDITIVE ? 56 : 48) : 88;
 #endif
 };
 #ifndef JSDE_DUO_STAGE_AHEAD

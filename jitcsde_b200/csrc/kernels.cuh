@@ -44,7 +44,7 @@ constexpr size_t duo_smem_bytes() { return ((size_t)DUO_PAIRS * PairLayout<Model
 // and, under the power cap, ~2 % clock when they do not (additive Lorenz to t = 100: step counts within 1 %), so the
 // host enables it for non-additive models (JSDE_RECYCLE=0/1 overrides).
 template <class Model, bool GRID, bool RECYCLE>
-__global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N>::BLOCKS) k_integrate(EnsembleView e, Controller c, double target, int use_tape,
+__global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE>::BLOCKS) k_integrate(EnsembleView e, Controller c, double target, int use_tape,
 	const double *__restrict__ grid_times_, int grid_count, double *__restrict__ grid_out)
 {
 	constexpr int N = Model::N;
@@ -55,14 +55,14 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N>::BLOCKS) k_inte
 	double *pair_smem = jsde_smem + MATH_TAB_DOUBLES + pair * PairLayout<N>::DOUBLES;
 
 	if (warp >= DUO_PAIRS) {  // ---- producer warpgroup ----
-		setmaxnreg_dec<DuoConfig<N>::PRODUCER_REGS>();
+		setmaxnreg_dec<DuoConfig<N, Model::ADDITIVE>::PRODUCER_REGS>();
 		PairProducer<N> P(pair_smem, pair, e.mt);
 		P.run(e.rng_spill, e.rng_level, e.mt_chunk, e.B);
 		return;
 	}
 
 	// ---- consumer warpgroup ----
-	setmaxnreg_inc<DuoConfig<N>::CONSUMER_REGS>();
+	setmaxnreg_inc<DuoConfig<N, Model::ADDITIVE>::CONSUMER_REGS>();
 	const double *grid_times = GRID ? grid_times_ : nullptr;  // compile-time nullptr keeps the plain kernel free of grid code
 	// Sampling-grid mode (grid_times != nullptr): the lane integrates to grid_times[0], records its state in
 	// grid_out[0][·][k], goes on to grid_times[1], … — exactly the sequence of integrate() calls of
