@@ -41,6 +41,14 @@ def test_philox4x32_10_known_answers():
 		assert list(out) == want
 
 
+def test_golden_variates():
+	import json
+	g = json.load(open(os.path.join(ROOT, "tests", "golden", "philox_jumps.json")))
+	taus, xis = host_tape(g["seed"], g["first"], 2, 4)
+	assert [[float(v).hex() for v in r] for r in taus] == g["taus"]
+	assert [[float(v).hex() for v in r] for r in xis] == g["xis"]
+
+
 def test_variates_are_what_they_claim():
 	taus, xis = host_tape(2024, 0, 64, 4000)
 	n = taus.size
