@@ -278,6 +278,7 @@ def run_gpu_arm(args):
 				"ms_per_step": wall / args.steps * 1e3},
 			"gpu_launches": launches, "clocks": clocks,
 			"accepted_per_step": accepted // args.steps, "rejected_per_step": rejected // args.steps, "failed_trajectories": failed,
+			"attempts_per_s": attempts / (kernel_ms * 1e-3), "accept_ratio": accepted / attempts if attempts else None,
 			"roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp64_peak,
 				"traffic": NCU_DRAM_BYTES_PER_ATTEMPT * attempts / args.steps / world,
 				"traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per attempt (B=2^18 steady-state capture, "
