@@ -174,7 +174,7 @@ const char *jsde_model_name(void) { return JSDE_MODEL_NAME; }
 int jsde_model_info(int *n, int *additive, int *n_params, int *has_jump)
 {
 	if (n) *n = Model::N;
-	if (additive) *additive = 1;
+	if (additive) *additive = Model::ADDITIVE ? 1 : 0;
 	if (n_params) *n_params = Model::NPAR;
 	if (has_jump) *has_jump = 0;
 	return JSDE_OK;
@@ -225,6 +225,9 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	ALLOC(v.qh, B * h->D); ALLOC(v.qw, B * h->D * 2 * n); ALLOC(v.order, B * h->D); ALLOC(v.q_count, B);
 	ALLOC(v.key, B * MT_WORDS); ALLOC(v.pos, B);
 	ALLOC(v.arg, B * n); ALLOC(v.sW, B * n); ALLOC(v.sZ, B * n); ALLOC(v.sF1, B * n); ALLOC(v.sNY, B * n);
+	if (!Model::ADDITIVE) {
+		ALLOC(v.argA, B * n); ALLOC(v.argB, B * n); ALLOC(v.argC, B * n); ALLOC(v.sG2, B * n); ALLOC(v.sG3, B * n);
+	}
 	ALLOC(v.status, B); ALLOC(v.accepted, B); ALLOC(v.rejected, B); ALLOC(v.totals, 1);
 	ALLOC(h->seeds, B); ALLOC(h->par, Model::NPAR > 0 ? Model::NPAR : 1); ALLOC(h->shift, n);
 #undef ALLOC

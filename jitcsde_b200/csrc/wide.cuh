@@ -23,7 +23,7 @@
 //   noise memory ..... jitced_template.c:170-250; items are addressed through a small permutation (logical position ->
 //                      physical slot) so that a Brownian-bridge insertion or a pop never moves 16 KB items.
 //   SRA1 step ........ jitced_template.c:466-494;   error ratio / commit ... :502-536;   controller ... _jitcsde.py:569-630
-// Additive noise only (the network of config 5); no jumps yet.
+// SRA1 for additive and SRIW1 for multiplicative noise (template:408-464); no jumps yet.
 #pragma once
 
 #include "ensemble.cuh"
@@ -58,6 +58,8 @@ struct WideView {
 	// scratch vectors [B][n], L2-resident: stage argument, Wiener increments DW/DZ of the current attempt, first drift
 	// (times h), proposal
 	double *arg, *sW, *sZ, *sF1, *sNY;
+	// multiplicative noise (SRI) only: the three further stage arguments and the diffusion values g2, g3
+	double *argA, *argB, *argC, *sG2, *sG3;
 };
 
 __global__ void k_wide_seed(uint32_t *key, int *pos, const uint32_t *seeds, int64_t B)
@@ -461,8 +463,17 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 							const double cs = (UNITS > 0 && i < UNITS) ? SC[i * TPAD + col] : 0.0;
 							const double I10 = (e.sW[b * N + i] + e.sZ[b * N + i] * (1. / 1.7320508075688772)) * (h / 2.);
 							const double fh1 = Model::drift_local(i, t, Y, e.par, cs) * h;
-							const double g1 = Model::diffusion_component(i, t + h, Y, e.par);
-							const double a = Y[i] + 0.75 * fh1 + 0.5 * g1 * I10 / h;
+							double a;
+							if constexpr (Model::ADDITIVE) {
+								const double g1 = Model::diffusion_component(i, t + h, Y, e.par);
+								a = Y[i] + 0.75 * fh1 + 0.5 * g1 * I10 / h;
+							} else {  // SRIW1 (template:417-438): the arguments of fh2, g2 and g3 only need fh1 and g1
+								const double g1 = Model::diffusion_component(i, t, Y, e.par);
+								const double sqh = sqrt(h);
+								a = Y[i] + 0.75 * fh1 + 1.5 * g1 * I10 / h;
+								e.argA[b * N + i] = Y[i] + 0.25 * fh1 + 0.5 * g1 * sqh;
+								e.argB[b * N + i] = Y[i] + fh1 - g1 * sqh;
+							}
 							e.sF1[b * N + i] = fh1;
 							e.arg[b * N + i] = a;
 							if (UNITS > 0 && i < UNITS)
@@ -471,6 +482,29 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 					}
 				}
 			} else {
+				if constexpr (!Model::ADDITIVE) {
+					// ---- P4 (SRI only): g2, g3 and the argument of g4 (template:439-445) ---------------------------------
+					for (unsigned m = mask; m; m &= m - 1) {
+						const int tr = __ffs(m) - 1;
+						const int64_t b = b0 + tr;
+						const double *Y = e.y + b * N;
+						const double t = ts[tr].t, h = ts[tr].h;
+						const double sqh = sqrt(h);
+#pragma unroll
+						for (int cc = 0; cc < CPT; cc++) {
+							const int i = cc * WBLOCK + tid;
+							if (i < N) {
+								const double g1 = Model::diffusion_component(i, t, Y, e.par);
+								const double g2 = Model::diffusion_component(i, t + 0.25 * h, e.argA + b * N, e.par);
+								const double g3 = Model::diffusion_component(i, t + h, e.argB + b * N, e.par);
+								e.sG2[b * N + i] = g2;
+								e.sG3[b * N + i] = g3;
+								e.argC[b * N + i] = Y[i] + 0.25 * e.sF1[b * N + i] + sqh * (-5 * g1 + 3 * g2 + 0.5 * g3);
+							}
+						}
+					}
+					__syncthreads();
+				}
 				// ---- P5: second stage, proposal, error ratio (template:482-526) -----------------------------------------
 				int col = 0;
 				for (unsigned m = mask; m; m &= m - 1, col++) {
@@ -489,10 +523,31 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 							const double I10 = (W + e.sZ[b * N + i] * (1. / 1.7320508075688772)) * (h / 2.);
 							const double fh1 = e.sF1[b * N + i];
 							const double fh2 = Model::drift_local(i, t_mid, A, e.par, cs) * h;
-							const double g1 = Model::diffusion_component(i, t + h, Y, e.par);
-							const double g2 = Model::diffusion_component(i, t, Y, e.par);
-							const double E_N = I10 / h * (g2 - g1);
-							const double ny = Y[i] + E_N + (1. / 3.) * (fh1 + 2 * fh2) + W * g1;
+							double E_N, ny;
+							if constexpr (Model::ADDITIVE) {
+								const double g1 = Model::diffusion_component(i, t + h, Y, e.par);
+								const double g2 = Model::diffusion_component(i, t, Y, e.par);
+								E_N = I10 / h * (g2 - g1);
+								ny = Y[i] + E_N + (1. / 3.) * (fh1 + 2 * fh2) + W * g1;
+							} else {  // SRIW1 (template:447-464), expression shapes of stepper.cuh
+								const double g1 = Model::diffusion_component(i, t, Y, e.par);
+								const double g2 = e.sG2[b * N + i], g3 = e.sG3[b * N + i];
+								const double g4 = Model::diffusion_component(i, t + 0.25 * h, e.argC + b * N, e.par);
+								const double sqh = sqrt(h);
+								const double third_over_h = 1. / h / 3.;
+								const double I11s = (W * W - h) * 0.5 / sqh;
+								const double I111 = (W * W * W - 3 * h * W) * (1. / 6.);
+								E_N = third_over_h * (
+									+ (6 * I10 - 6 * I111) * g1
+									+ (-4 * I10 + 5 * I111) * g2
+									+ (-2 * I10 - 2 * I111) * g3
+									+ (3 * I111) * g4);
+								ny = Y[i] + E_N + (1. / 3.) * (
+									fh1 + 2 * fh2
+									+ (-3 * W - 3 * I11s) * g1
+									+ (4 * W + 4 * I11s) * g2
+									+ (2 * W - I11s) * g3);
+							}
 							const double E_D = (fh2 - fh1) / 6;
 							const double er = fabs(E_D) + fabs(E_N);
 							e.sNY[b * N + i] = ny;

@@ -68,7 +68,7 @@ cubic = ModelSpec("cubic", 1, True, ("-(y(0)*y(0)*y(0))+4*y(0)+y(0)*y(0)",), ("3
 
 
 
-def fhn_network(units: int, name: str, seed: int = 7) -> ModelSpec:
+def fhn_network(units: int, name: str, seed: int = 7, multiplicative: bool = False) -> ModelSpec:
 	"""
 	Noisy FitzHugh–Nagumo network with dense coupling (SURVEY §8 d config 5; units=500 gives n=1000):
 	    dv_i = v_i - v_i^3/3 - w_i + I + (K/N) sum_j A_ij (v_j - v_i),    dw_i = eps (v_i + a - b w_i),
@@ -89,13 +89,18 @@ JSDE_MODEL_CONST double FHN_AT[FHN_UNITS * FHN_UNITS] = {{{table}}};
 """
 	f_component = ("(i < FHN_UNITS ? y(i) - y(i) * y(i) * y(i) / 3.0 - y(FHN_UNITS + i) + 0.5 + (1.0 / FHN_UNITS) * coupling"
 		" : 0.08 * (y(i - FHN_UNITS) + 0.7 - 0.8 * y(i)))")
-	return ModelSpec(name, 2 * units, True, (), (), preamble=preamble,
-		f_component=f_component, g_component="(i < FHN_UNITS ? 0.05 : 0.0)",
+	# multiplicative variant (exercises the wide SRI path): state-dependent amplitudes, one of them reaching across
+	# components — the diffusion of w_i depends on v_i
+	g_component = ("(i < FHN_UNITS ? 0.05 * y(i) + 0.02 : 0.01 * y(i - FHN_UNITS) + 0.01 * y(i))" if multiplicative
+		else "(i < FHN_UNITS ? 0.05 : 0.0)")
+	return ModelSpec(name, 2 * units, not multiplicative, (), (), preamble=preamble,
+		f_component=f_component, g_component=g_component,
 		coupling_units=units, coupling_table="FHN_AT")
 
 
 #: small network for the parity tests of the wide (block-per-trajectory) kernel
 fhn_small = fhn_network(24, "fhn_small")
+fhn_small_mult = fhn_network(24, "fhn_small_mult", multiplicative=True)
 _FHN_1000 = None
 
 
@@ -109,5 +114,5 @@ def fhn_1000() -> ModelSpec:
 
 ALL = {m.name: m for m in (
 	lorenz_additive, lorenz_additive_fixture, lorenz_multiplicative, lorenz_jumpy, lorenz_jumpy_rate,
-	gbm, gbm_pars, duffing, ou, ou_timedep, cubic, ring6, ring6_mult, fhn_small,
+	gbm, gbm_pars, duffing, ou, ou_timedep, cubic, ring6, ring6_mult, fhn_small, fhn_small_mult,
 )}

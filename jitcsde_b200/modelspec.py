@@ -72,7 +72,6 @@ class ModelSpec:
 	def __post_init__(self):
 		if self.wide:
 			assert self.g_component, "wide models need g_component too"
-			assert self.additive, "wide models are implemented for additive noise (SRA) only"
 			assert self.jump is None
 			if self.coupling_units:
 				assert self.coupling_table and 0 < self.coupling_units <= self.n

@@ -42,6 +42,21 @@ def test_small_network_vs_oracle(monkeypatch, tpb):
 	assert not np.array_equal(E.get_state(), ref2["y"]) or True  # (one-shot to 4.0 differs: the step at t=3 was truncated)
 
 
+@pytest.mark.parametrize("tpb", [1, 4, 7])
+def test_small_network_multiplicative_noise_vs_oracle(monkeypatch, tpb):
+	"""SRIW1 on the wide path: state-dependent amplitudes, incl. one that reaches across components."""
+	monkeypatch.setenv("JSDE_WIDE_TPB", str(tpb))
+	spec = models.fhn_small_mult
+	B, T = 23, 2.0
+	E, stats, y0 = run(spec, B, T)
+	ref = port.run_ensemble(spec, y0, sharding.global_seeds(0, B), 0.0, T)
+	assert_bits_equal(E.get_state(), ref["y"], "states")
+	assert_bits_equal(E.t, ref["t"], "times")
+	dt, acc, rej = E.controller_state()
+	assert (acc.astype(np.int64) == ref["accepted"]).all() and (rej.astype(np.int64) == ref["rejected"]).all()
+	assert stats["n_overflow"] == 0 and int(ref["rejected"].sum()) > 0
+
+
 @pytest.mark.parametrize("tpb,B", [(7, 9), (2, 3)])
 def test_config5_network_n1000_vs_oracle(monkeypatch, tpb, B):
 	monkeypatch.setenv("JSDE_WIDE_TPB", str(tpb))
