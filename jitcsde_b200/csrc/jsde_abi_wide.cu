@@ -65,6 +65,9 @@ struct jsde_handle {
 	double first_step = 1.0;
 	uint32_t *seeds = nullptr;
 	double *par = nullptr, *shift = nullptr;
+	double *taus = nullptr, *xis = nullptr;
+	const double *tape_src_taus = nullptr, *tape_src_xis = nullptr;
+	long long tape_len = 0;
 	std::vector<void *> allocations;
 };
 
@@ -93,6 +96,8 @@ int reset_integrator(jsde_handle *h)
 	CU(cudaMemsetAsync(h->v.status, 0, B * sizeof(int), h->stream));
 	CU(cudaMemsetAsync(h->v.accepted, 0, B * sizeof(unsigned long long), h->stream));
 	CU(cudaMemsetAsync(h->v.rejected, 0, B * sizeof(unsigned long long), h->stream));
+	CU(cudaMemsetAsync(h->v.jump_set, 0, B, h->stream));
+	CU(cudaMemsetAsync(h->v.tape_pos, 0, B * sizeof(long long), h->stream));
 	k_iota_rows<<<grid_for(B * h->D, 256), 256, 0, h->stream>>>(h->v.order, B, h->D);
 	k_wide_seed<<<grid_for(B, 64), 64, 0, h->stream>>>(h->v.key, h->v.pos, h->seeds, B);
 	CU(cudaGetLastError());
@@ -135,7 +140,7 @@ int read_totals(jsde_handle *h, jsde_stats *stats_host)
 		stats_host->accepted = tot.accepted;
 		stats_host->rejected = tot.rejected;
 		stats_host->fresh_draws = tot.fresh_draws;
-		stats_host->jumps = 0;
+		stats_host->jumps = tot.jumps;
 		stats_host->n_min_step = tot.n_min_step;
 		stats_host->n_overflow = tot.n_overflow;
 		stats_host->max_noise_depth = tot.max_depth;
@@ -176,7 +181,7 @@ int jsde_model_info(int *n, int *additive, int *n_params, int *has_jump)
 	if (n) *n = Model::N;
 	if (additive) *additive = Model::ADDITIVE ? 1 : 0;
 	if (n_params) *n_params = Model::NPAR;
-	if (has_jump) *has_jump = 0;
+	if (has_jump) *has_jump = Model::HAS_JUMP ? 1 : 0;
 	return JSDE_OK;
 }
 
@@ -225,6 +230,7 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	ALLOC(v.qh, B * h->D); ALLOC(v.qw, B * h->D * 2 * n); ALLOC(v.order, B * h->D); ALLOC(v.q_count, B);
 	ALLOC(v.key, B * MT_WORDS); ALLOC(v.pos, B);
 	ALLOC(v.arg, B * n); ALLOC(v.sW, B * n); ALLOC(v.sZ, B * n); ALLOC(v.sF1, B * n); ALLOC(v.sNY, B * n);
+	ALLOC(v.next_jump, B); ALLOC(v.jump_set, B); ALLOC(v.tape_pos, B);
 	if (!Model::ADDITIVE) {
 		ALLOC(v.argA, B * n); ALLOC(v.argB, B * n); ALLOC(v.argC, B * n); ALLOC(v.sG2, B * n); ALLOC(v.sG3, B * n);
 	}
@@ -323,10 +329,91 @@ int jsde_integrate(jsde_t *h, double target_time, jsde_stats *stats_host)
 		return fail(JSDE_E_ARG, "Wrong input.");
 	int rc = bind(h);
 	if (rc) return rc;
+	h->v.use_jumps = 0;
 	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
 	CU(cudaEventRecord(h->ev0, h->stream));
 	if ((rc = launch_integrate(h, target_time))) return rc;
 	return read_totals(h, stats_host);
+}
+
+namespace {
+int upload_tape(jsde_handle *h, const jsde_jump_tape *tape)
+{
+	if (tape->taus_host != h->tape_src_taus || tape->xis_host != h->tape_src_xis || tape->length != h->tape_len) {
+		const size_t count = (size_t)h->B * (size_t)tape->length;
+		int rc;
+		if ((rc = dev_alloc(h, &h->taus, count)) || (rc = dev_alloc(h, &h->xis, count))) return rc;
+		CU(cudaMemcpyAsync(h->taus, tape->taus_host, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+		CU(cudaMemcpyAsync(h->xis, tape->xis_host, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+		h->tape_src_taus = tape->taus_host;
+		h->tape_src_xis = tape->xis_host;
+		h->tape_len = tape->length;
+	}
+	h->v.taus = h->taus;
+	h->v.xis = h->xis;
+	h->v.tape_len = h->tape_len;
+	h->v.use_jumps = 1;
+	h->v.generated_jumps = 0;
+	return JSDE_OK;
+}
+}  // namespace
+
+// jitcsde_jump.integrate (_jitcsde.py:693-700) with the variates from a tape …
+int jsde_integrate_jumps(jsde_t *h, double target_time, const jsde_jump_tape *tape, jsde_stats *stats_host)
+{
+	if (!h || !tape || tape->length < 0 || (tape->length > 0 && (!tape->taus_host || !tape->xis_host)) || !(target_time == target_time))
+		return fail(JSDE_E_ARG, "Wrong input.");
+	if (!Model::HAS_JUMP)
+		return fail(JSDE_E_STATE, "this model was generated without a jump amplitude");
+	int rc = bind(h);
+	if (rc) return rc;
+	if ((rc = upload_tape(h, tape))) return rc;
+	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
+	CU(cudaEventRecord(h->ev0, h->stream));
+	if ((rc = launch_integrate(h, target_time))) return rc;
+	return read_totals(h, stats_host);
+}
+
+// … or from the counter-based generator (csrc/philox_jumps.h)
+int jsde_integrate_jumps_generated(jsde_t *h, double target_time, uint64_t seed, int64_t first_index, jsde_stats *stats_host)
+{
+	if (!h || first_index < 0 || !(target_time == target_time))
+		return fail(JSDE_E_ARG, "Wrong input.");
+	if (!Model::HAS_JUMP)
+		return fail(JSDE_E_STATE, "this model was generated without a jump amplitude");
+	int rc = bind(h);
+	if (rc) return rc;
+	h->v.use_jumps = 1;
+	h->v.generated_jumps = 1;
+	h->v.jump_seed = seed;
+	h->v.jump_first = first_index;
+	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
+	CU(cudaEventRecord(h->ev0, h->stream));
+	if ((rc = launch_integrate(h, target_time))) return rc;
+	return read_totals(h, stats_host);
+}
+
+int jsde_generated_jump_tape(int device, uint64_t seed, int64_t first_index, int64_t count, int64_t length, double *taus_host, double *xis_host)
+{
+	if (first_index < 0 || count < 0 || length < 0 || !taus_host || !xis_host)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	if (count * length == 0)
+		return JSDE_OK;
+	CU(cudaSetDevice(device));
+	const size_t bytes = (size_t)count * (size_t)length * sizeof(double);
+	double *taus = nullptr, *xis = nullptr;
+	cudaError_t err = cudaMalloc(&taus, bytes);
+	if (err == cudaSuccess) err = cudaMalloc(&xis, bytes);
+	if (err == cudaSuccess) {
+		k_wide_jump_tape<<<grid_for(count * length, 256), 256>>>(seed, first_index, count, length, taus, xis);
+		err = cudaGetLastError();
+	}
+	if (err == cudaSuccess) err = cudaMemcpy(taus_host, taus, bytes, cudaMemcpyDeviceToHost);
+	if (err == cudaSuccess) err = cudaMemcpy(xis_host, xis, bytes, cudaMemcpyDeviceToHost);
+	cudaFree(taus); cudaFree(xis);
+	if (err != cudaSuccess)
+		return fail(JSDE_E_CUDA, cudaGetErrorString(err));
+	return JSDE_OK;
 }
 
 // the caller's sampling loop `for time in times: integrate(time)` (examples/noisy_lorenz.py:95-96) in one launch;
@@ -335,13 +422,15 @@ int jsde_integrate_grid(jsde_t *h, const double *times_host, int64_t n_times, co
 {
 	if (!h || !times_host || n_times <= 0 || n_times > 0x7fffffff || !y_host)
 		return fail(JSDE_E_ARG, "Wrong input.");
-	if (tape)
-		return unsupported("jumps");
+	if (tape && !Model::HAS_JUMP)
+		return fail(JSDE_E_STATE, "this model was generated without a jump amplitude");
 	for (int64_t j = 0; j < n_times; j++)
 		if (!(times_host[j] == times_host[j]))
 			return fail(JSDE_E_ARG, "Wrong input. (sample time is NaN)");
 	int rc = bind(h);
 	if (rc) return rc;
+	h->v.use_jumps = 0;
+	if (tape && (rc = upload_tape(h, tape))) return rc;
 	const size_t count = (size_t)n_times * (size_t)h->B * Model::N;
 	double *times = nullptr, *out = nullptr;
 	CU(cudaMalloc(&times, n_times * sizeof(double)));
@@ -422,9 +511,6 @@ int jsde_set_time(jsde_t *h, const double *t_host)
 
 int jsde_pin_noise(jsde_t *, unsigned, double) { return unsupported("pin_noise"); }
 int jsde_pin_noise_path(jsde_t *, unsigned, const double *, const double *, const double *) { return unsupported("pin_noise_path"); }
-int jsde_integrate_jumps(jsde_t *, double, const jsde_jump_tape *, jsde_stats *) { return unsupported("jumps"); }
-int jsde_integrate_jumps_generated(jsde_t *, double, uint64_t, int64_t, jsde_stats *) { return unsupported("jumps"); }
-int jsde_generated_jump_tape(int, uint64_t, int64_t, int64_t, int64_t, double *, double *) { return unsupported("jumps"); }
 int jsde_get_next_step(jsde_t *, const double *) { return unsupported("the single-step surface"); }
 int jsde_get_p(jsde_t *, double, double, double *) { return unsupported("the single-step surface"); }
 int jsde_accept_step(jsde_t *, const uint8_t *) { return unsupported("the single-step surface"); }
@@ -453,6 +539,7 @@ std::vector<std::pair<void *, size_t>> checkpoint_sections(jsde_handle *h)
 	return {
 		{v.y, B * n * 8}, {v.t, B * 8}, {v.dt, B * 8}, {v.qh, B * D * 8}, {v.qw, B * D * 2 * n * 8}, {v.order, B * D * 4},
 		{v.q_count, B * 4}, {v.key, B * MT_WORDS * 4}, {v.pos, B * 4}, {v.status, B * 4}, {v.accepted, B * 8}, {v.rejected, B * 8},
+		{v.next_jump, B * 8}, {v.jump_set, B}, {v.tape_pos, B * 8},
 		{h->seeds, B * 4}, {h->par, (size_t)(Model::NPAR > 0 ? Model::NPAR : 1) * 8},
 	};
 }

@@ -23,12 +23,13 @@
 //   noise memory ..... jitced_template.c:170-250; items are addressed through a small permutation (logical position ->
 //                      physical slot) so that a Brownian-bridge insertion or a pop never moves 16 KB items.
 //   SRA1 step ........ jitced_template.c:466-494;   error ratio / commit ... :502-536;   controller ... _jitcsde.py:569-630
-// SRA1 for additive and SRIW1 for multiplicative noise (template:408-464); no jumps yet.
+// SRA1 for additive and SRIW1 for multiplicative noise (template:408-464); jumps from a tape or a counter-based generator.
 #pragma once
 
 #include "ensemble.cuh"
 #include "gauss.cuh"
 #include "mt19937.cuh"
+#include "philox_jumps.h"
 
 namespace jsde {
 namespace wide {
@@ -60,6 +61,15 @@ struct WideView {
 	double *arg, *sW, *sZ, *sF1, *sNY;
 	// multiplicative noise (SRI) only: the three further stage arguments and the diffusion values g2, g3
 	double *argA, *argB, *argC, *sG2, *sG3;
+	// jumps (jitcsde_jump.integrate, _jitcsde.py:682-700): scheduling state per trajectory and the source of the variates
+	double *next_jump;        // [B]
+	unsigned char *jump_set;  // [B]
+	long long *tape_pos;      // [B]
+	const double *taus, *xis; // [B][tape_len] (tape mode)
+	long long tape_len;
+	int use_jumps, generated_jumps;
+	unsigned long long jump_seed;
+	long long jump_first;
 };
 
 __global__ void k_wide_seed(uint32_t *key, int *pos, const uint32_t *seeds, int64_t B)
@@ -86,7 +96,12 @@ struct TrajShared {
 	int pos, count, cursor, status, running, last, accept, max_depth;
 	unsigned acc, rej, fresh;
 	int grid_index, sample_slot;  // sampling-grid mode: next sample time, and (>= 0) the sample the commit phase records
-	int pad_;
+	// jumps: time of the next one (valid if jump_set), jumps applied so far (index into the tape / counter of the
+	// generator), whether the step under way ends at a jump, whether a jump is due on the state P7 has just committed
+	double next_jump;
+	long long tape_pos;
+	int jump_set, to_jump, pending_jump;
+	unsigned jumps;
 };
 
 // The reference's batch twist (random_numbers.c:73-84) by ONE warp on a state in shared memory.  Within a phase,
@@ -238,8 +253,17 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 				S.target = grid_times ? grid_times[0] : target;
 				S.grid_index = 0;
 				S.sample_slot = -1;
-				// integrate() with nothing to do (:614) returns at once; in grid mode that is decided per sample in P1
-				S.running = status == TRAJ_OK && (grid_times != nullptr || !(S.t >= target));
+				// integrate() with nothing to do (:614), sample times already reached and due jumps are handled in P1
+				S.running = status == TRAJ_OK;
+				S.next_jump = 0.0;
+				S.tape_pos = 0;
+				S.jump_set = S.to_jump = S.pending_jump = 0;
+				S.jumps = 0;
+				if (Model::HAS_JUMP && e.use_jumps) {
+					S.next_jump = e.next_jump[b];
+					S.jump_set = e.jump_set[b] != 0;
+					S.tape_pos = e.tape_pos[b];
+				}
 				S.acc = S.rej = S.fresh = 0;
 				S.max_depth = 0;
 				S.cursor = 0;
@@ -249,6 +273,8 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			S.running = 0;
 			S.accept = 0;
 			S.sample_slot = -1;
+			S.jumps = 0;
+			S.pending_jump = 0;
 			S.status = TRAJ_OK;
 			S.acc = S.rej = S.fresh = 0;
 			S.max_depth = 0;
@@ -274,34 +300,87 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			double *const qw = e.qw + b * D * 2 * N;
 			double *const sW = e.sW + b * N, *const sZ = e.sZ + b * N;
 			const double t = S.t, dt = S.dt;
-			double goal = S.target;
-			if (grid_times) {  // sample times that are already reached: record the state as it is (integrate() is a no-op)
-				int gi = S.grid_index;
-				while (gi < grid_count && t >= goal) {
-					const double *Y = e.y + b * N;
+			// ---- what to integrate to (_jitcsde.py:614, :682-700; the sampling loop of examples/noisy_lorenz.py:95-96):
+			// apply a jump that is due, schedule the next one, record sample times that are already reached — until an
+			// attempt is due or the trajectory is done.  Every lane runs this on identical inputs; lane 0 publishes.
+			double cur_target = S.target, tgt = cur_target, next_jump = S.next_jump;
+			int gi = S.grid_index, jump_set = S.jump_set;
+			long long tape_pos = S.tape_pos;
+			unsigned jumped = 0;
+			bool to_jump = false, apply = S.pending_jump != 0, still_running = true;
+			double *const Ycur = e.y + b * N;
+			while (true) {
+				if (Model::HAS_JUMP && apply) {  // apply_jump(amp(time, state)) (:696-698) on the pre-jump state
+					const double xi = e.generated_jumps ? jsde_jump_xi(e.jump_seed, e.jump_first + b, tape_pos) : e.xis[b * e.tape_len + tape_pos];
+					double *const change = e.sNY + b * N;
+					for (int i = lane; i < N; i += 32)
+						change[i] = Model::jump_component(i, t, Ycur, xi, e.par);
+					__syncwarp();
+					for (int i = lane; i < N; i += 32)
+						Ycur[i] += change[i];
+					__syncwarp();
+					tape_pos++;
+					jumped++;
+					jump_set = 0;
+					apply = false;
+				}
+				tgt = cur_target;
+				to_jump = false;
+				if (Model::HAS_JUMP && e.use_jumps) {
+					if (!jump_set) {  // next_jump property (:682-687): t + IJI(t, y)
+						double wait = __longlong_as_double(0x7ff0000000000000LL);  // past the end of a tape: no further jumps
+						if (e.generated_jumps)
+							wait = Model::waiting_time(t, Ycur, jsde_jump_tau(e.jump_seed, e.jump_first + b, tape_pos), e.par);
+						else if (tape_pos < e.tape_len)
+							wait = Model::waiting_time(t, Ycur, e.taus[b * e.tape_len + tape_pos], e.par);
+						next_jump = t + wait;
+						jump_set = 1;
+					}
+					if (next_jump < cur_target) {
+						tgt = next_jump;
+						to_jump = true;
+					}
+				}
+				if (!(t >= tgt))
+					break;  // an attempt is due
+				if (to_jump) {
+					apply = true;
+					continue;
+				}
+				if (grid_times) {  // this sample time is reached without a step: integrate() is a no-op, record the state
 					double *out = grid_out + ((int64_t)gi * e.B + b) * N;
 					for (int i = lane; i < N; i += 32)
-						out[i] = Y[i];
+						out[i] = Ycur[i];
 					gi++;
-					if (gi < grid_count)
-						goal = grid_times[gi];
+					if (gi < grid_count) {
+						cur_target = grid_times[gi];
+						continue;
+					}
 				}
-				__syncwarp();
-				if (lane == 0) {
-					S.grid_index = gi;
-					S.target = goal;
-					if (gi >= grid_count)
-						S.running = 0;
-				}
-				__syncwarp();
+				still_running = false;
+				break;
 			}
-			if (S.running) {
+			__syncwarp();
+			if (lane == 0) {
+				S.grid_index = gi;
+				S.target = cur_target;
+				S.next_jump = next_jump;
+				S.jump_set = jump_set;
+				S.tape_pos = tape_pos;
+				S.to_jump = to_jump;
+				S.pending_jump = 0;
+				S.jumps += jumped;
+				if (!still_running)
+					S.running = 0;
+			}
+			__syncwarp();
+			if (still_running) {
 			double h;
 			bool last = false;
-			if (t + dt < goal)
+			if (t + dt < tgt)
 				h = dt;
 			else {
-				h = goal - t;
+				h = tgt - t;
 				last = true;
 			}
 			int count = S.count, pos = S.pos;
@@ -618,7 +697,9 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 					S.t = S.t + h;
 					S.acc++;
 					S.accept = 1;
-					if (S.last) {
+					if (S.last && S.to_jump)
+						S.pending_jump = 1;  // the step ended at a jump time: applied on the committed state at the next P1
+					else if (S.last) {
 						if (grid_times) {  // the commit phase records this sample; then on to the next sample time
 							S.sample_slot = S.grid_index;
 							S.grid_index++;
@@ -674,6 +755,12 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			e.status[b] = S.status;
 			e.accepted[b] += S.acc;
 			e.rejected[b] += S.rej;
+			if (Model::HAS_JUMP && e.use_jumps) {
+				e.next_jump[b] = S.next_jump;
+				e.jump_set[b] = S.jump_set ? 1 : 0;
+				e.tape_pos[b] = S.tape_pos;
+			}
+			if (S.jumps) atomicAdd(&e.totals->jumps, (unsigned long long)S.jumps);
 			if (S.acc) atomicAdd(&e.totals->accepted, (unsigned long long)S.acc);
 			if (S.rej) atomicAdd(&e.totals->rejected, (unsigned long long)S.rej);
 			if (S.fresh) atomicAdd(&e.totals->fresh_draws, (unsigned long long)S.fresh);
@@ -682,6 +769,17 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			atomicMax(&e.totals->max_depth, S.max_depth);
 		}
 	}
+}
+
+// the counter-based jump variates as a tape: taus, xis [count][length] for trajectories first .. first+count-1
+__global__ void k_wide_jump_tape(unsigned long long seed, long long first, long long count, long long length, double *taus, double *xis)
+{
+	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= count * length)
+		return;
+	const long long k = idx / length, j = idx - k * length;
+	taus[idx] = jsde_jump_tau(seed, first + k, j);
+	xis[idx] = jsde_jump_xi(seed, first + k, j);
 }
 
 __global__ void k_iota_rows(int *order, int64_t B, int D)

@@ -68,7 +68,7 @@ cubic = ModelSpec("cubic", 1, True, ("-(y(0)*y(0)*y(0))+4*y(0)+y(0)*y(0)",), ("3
 
 
 
-def fhn_network(units: int, name: str, seed: int = 7, multiplicative: bool = False) -> ModelSpec:
+def fhn_network(units: int, name: str, seed: int = 7, multiplicative: bool = False, jumpy: bool = False) -> ModelSpec:
 	"""
 	Noisy FitzHugh–Nagumo network with dense coupling (SURVEY §8 d config 5; units=500 gives n=1000):
 	    dv_i = v_i - v_i^3/3 - w_i + I + (K/N) sum_j A_ij (v_j - v_i),    dw_i = eps (v_i + a - b w_i),
@@ -93,14 +93,17 @@ JSDE_MODEL_CONST double FHN_AT[FHN_UNITS * FHN_UNITS] = {{{table}}};
 	# components — the diffusion of w_i depends on v_i
 	g_component = ("(i < FHN_UNITS ? 0.05 * y(i) + 0.02 : 0.01 * y(i - FHN_UNITS) + 0.01 * y(i))" if multiplicative
 		else "(i < FHN_UNITS ? 0.05 : 0.0)")
+	# jumpy variant (exercises jumps on the wide path): kicks on the v components, intensity growing with v_0^2
+	jump = JumpSpec(("(i < FHN_UNITS ? 0.2 * xi * (1.0 + y(i)) : 0.0)",), iji="tau/(2.0+y(0)*y(0))") if jumpy else None
 	return ModelSpec(name, 2 * units, not multiplicative, (), (), preamble=preamble,
-		f_component=f_component, g_component=g_component,
+		f_component=f_component, g_component=g_component, jump=jump,
 		coupling_units=units, coupling_table="FHN_AT")
 
 
 #: small network for the parity tests of the wide (block-per-trajectory) kernel
 fhn_small = fhn_network(24, "fhn_small")
 fhn_small_mult = fhn_network(24, "fhn_small_mult", multiplicative=True)
+fhn_small_jumpy = fhn_network(24, "fhn_small_jumpy", jumpy=True)
 _FHN_1000 = None
 
 
@@ -114,5 +117,5 @@ def fhn_1000() -> ModelSpec:
 
 ALL = {m.name: m for m in (
 	lorenz_additive, lorenz_additive_fixture, lorenz_multiplicative, lorenz_jumpy, lorenz_jumpy_rate,
-	gbm, gbm_pars, duffing, ou, ou_timedep, cubic, ring6, ring6_mult, fhn_small, fhn_small_mult,
+	gbm, gbm_pars, duffing, ou, ou_timedep, cubic, ring6, ring6_mult, fhn_small, fhn_small_mult, fhn_small_jumpy,
 )}

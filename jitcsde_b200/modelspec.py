@@ -72,7 +72,7 @@ class ModelSpec:
 	def __post_init__(self):
 		if self.wide:
 			assert self.g_component, "wide models need g_component too"
-			assert self.jump is None
+			assert self.jump is None or len(self.jump.amp) == 1, "wide models: ONE jump-amplitude expression in the component index i"
 			if self.coupling_units:
 				assert self.coupling_table and 0 < self.coupling_units <= self.n
 				u, tab = self.coupling_units, self.coupling_table

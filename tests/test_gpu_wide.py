@@ -94,6 +94,47 @@ def test_wide_sampling_grid_equals_repeated_calls(monkeypatch, tpb):
 	assert_bits_equal(E.get_state(), F.get_state(), "continued")
 
 
+@pytest.mark.parametrize("tpb", [1, 7])
+def test_wide_jumps_vs_oracle(monkeypatch, tpb):
+	"""Jumps on the wide path (tape): kicks with a state-dependent intensity, two consecutive calls; then the tape-free
+	counter-based variates against their replay; then the sampling grid with jumps against repeated calls."""
+	from jitcsde_b200 import _abi
+	from util import jump_tape
+	monkeypatch.setenv("JSDE_WIDE_TPB", str(tpb))
+	spec = models.fhn_small_jumpy
+	B = 17
+	taus, xis = jump_tape(B, 64)
+	E, _, y0 = run(spec, B, 0.0)
+	st = E.integrate_jumps(1.0, taus, xis)
+	E.integrate_jumps(2.2, taus, xis)
+	assert st["jumps"] > B
+	ref = port.run_ensemble(spec, y0, sharding.global_seeds(0, B), 0.0, 1.0, taus=taus, xis=xis)
+	y = E.get_state()
+	for k in range(0, B, 4):
+		P = port.PortCore(spec, y0[k], 0.0, k)
+		P.integrate_jumps(1.0, taus[k], xis[k])
+		if k == 0:
+			assert_bits_equal(ref["y"][0], P.get_state(), "port ensemble vs single")
+		P.integrate_jumps(2.2, taus[k], xis[k])
+		assert_bits_equal(y[k], P.get_state(), f"trajectory {k}")
+	# tape-free == replay of the generated tape
+	lib = _abi.load_library(spec)
+	gt, gx = _abi.generated_jump_tape(lib, 99, 5, B, 400)
+	A, _, _ = run(spec, B, 0.0)
+	R, _, _ = run(spec, B, 0.0)
+	A.integrate_jumps_generated(1.5, 99, 5)
+	R.integrate_jumps(1.5, gt, gx)
+	assert_bits_equal(A.get_state(), R.get_state(), "tape-free vs replay")
+	# sampling grid with jumps == repeated calls
+	times = np.array([0.3, 0.3, 0.9, 1.7])
+	G, _, _ = run(spec, B, 0.0)
+	grid = G.integrate_grid(times, taus, xis)
+	F, _, _ = run(spec, B, 0.0)
+	for j, tj in enumerate(times):
+		F.integrate_jumps(float(tj), taus, xis)
+		assert_bits_equal(grid[j], F.get_state(), f"sample {j}")
+
+
 def test_wide_checkpoint_restore():
 	spec = models.fhn_small
 	B = 11
@@ -114,6 +155,8 @@ def test_wide_failure_paths_and_unsupported_calls():
 	assert stats["n_min_step"] == 4 and (E.status == 1).all()
 	with pytest.raises(JsdeError, match="not implemented for wide"):
 		E.pin_noise(1, 1e-3)
+	with pytest.raises(JsdeError, match="without a jump amplitude"):
+		E.integrate_jumps(1.0, np.ones((4, 2)), np.ones((4, 2)))
 	with pytest.raises(JsdeError, match="not implemented for wide"):
 		E.get_next_step(1e-3)
 
