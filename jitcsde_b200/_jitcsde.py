@@ -437,7 +437,7 @@ class jitcsde_jump(jitcsde):
 
 	def check(self, fail_fast=True):
 		super().check(fail_fast)
-		if len(self.spec.jump.amp) != self.n:
+		if not self.spec.wide and len(self.spec.jump.amp) != self.n:  # wide models: one expression in the component index
 			raise ValueError("Output of amp function has the wrong dimension")
 
 
