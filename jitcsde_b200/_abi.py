@@ -39,6 +39,7 @@ class Stats(ctypes.Structure):
 		("accepted", ctypes.c_ulonglong), ("rejected", ctypes.c_ulonglong), ("fresh_draws", ctypes.c_ulonglong),
 		("jumps", ctypes.c_ulonglong), ("n_min_step", ctypes.c_longlong), ("n_overflow", ctypes.c_longlong),
 		("max_noise_depth", ctypes.c_int), ("kernel_launches", ctypes.c_int), ("kernel_ms", ctypes.c_float),
+		("n_tape_exhausted", ctypes.c_longlong),
 	]
 
 	def as_dict(self):
@@ -52,7 +53,8 @@ class JumpTape(ctypes.Structure):
 #: every symbol include/jsde.h declares (tests/test_abi_symbols.py checks the built library exports them all)
 ABI_SYMBOLS = (
 	"jsde_model_info", "jsde_model_name", "jsde_create", "jsde_destroy", "jsde_set_state", "jsde_seed",
-	"jsde_set_integration_parameters", "jsde_set_parameters", "jsde_pin_noise", "jsde_integrate", "jsde_integrate_jumps", "jsde_integrate_grid",
+	"jsde_set_integration_parameters", "jsde_set_parameters", "jsde_pin_noise", "jsde_integrate", "jsde_set_jump_tape", "jsde_integrate_jumps",
+	"jsde_integrate_grid", "jsde_integrate_grid_jumps",
 	"jsde_get_state", "jsde_get_controller_state", "jsde_moments", "jsde_get_next_step", "jsde_get_p", "jsde_accept_step",
 	"jsde_apply_jump", "jsde_set_time", "jsde_draw_gauss_debug", "jsde_dump_noise", "jsde_measure_fp64_peak",
 	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_shared_div", "jsde_debug_inline_math", "jsde_pin_noise_path", "jsde_integrate_jumps_generated", "jsde_generated_jump_tape", "jsde_checkpoint_bytes", "jsde_checkpoint_save", "jsde_checkpoint_restore", "jsde_last_error", "jsde_version",
@@ -75,6 +77,11 @@ def _declare(lib):
 	lib.jsde_integrate.argtypes = [H, ctypes.c_double, ctypes.POINTER(Stats)]
 	lib.jsde_integrate_jumps.argtypes = [H, ctypes.c_double, ctypes.POINTER(JumpTape), ctypes.POINTER(Stats)]
 	lib.jsde_integrate_grid.argtypes = [H, c_double_p, ctypes.c_int64, ctypes.POINTER(JumpTape), c_double_p, ctypes.POINTER(Stats)]
+	lib.jsde_set_jump_tape.argtypes = [H, ctypes.POINTER(JumpTape)]
+	lib.jsde_integrate_grid_jumps.argtypes = [H, c_double_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint64, ctypes.c_int64, c_double_p, ctypes.POINTER(Stats)]
+	lib.jsde_integrate_jumps_generated.argtypes = [H, ctypes.c_double, ctypes.c_uint64, ctypes.c_int64, ctypes.POINTER(Stats)]
+	lib.jsde_pin_noise_path.argtypes = [H, ctypes.c_uint, c_double_p, c_double_p, c_double_p]
+	lib.jsde_generated_jump_tape.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_double_p, c_double_p]
 	lib.jsde_get_state.argtypes = [H, c_double_p, c_double_p, c_i32_p]
 	lib.jsde_get_controller_state.argtypes = [H, c_double_p, c_u64_p, c_u64_p]
 	lib.jsde_moments.argtypes = [H, ctypes.c_void_p, c_double_p]
@@ -147,7 +154,7 @@ class Ensemble:
 			raise JsdeError("library does not match the model description")
 		self._h = ctypes.c_void_p()
 		self._check(self.lib.jsde_create(ctypes.byref(self._h), device, self.B, noise_capacity))
-		self._tape = None
+		self.has_tape = False
 		self.last_stats = None
 
 	def _check(self, rc):
@@ -211,7 +218,6 @@ class Ensemble:
 		if dw.shape != (self.B, steps.size, self.n) or dz.shape != dw.shape:
 			raise ValueError("dw and dz must have shape [B][len(steps)][n]")
 		dw, dz = np.ascontiguousarray(dw), np.ascontiguousarray(dz)
-		self.lib.jsde_pin_noise_path.argtypes = [ctypes.c_void_p, ctypes.c_uint, c_double_p, c_double_p, c_double_p]
 		self._check(self.lib.jsde_pin_noise_path(self._h, steps.size, _dp(steps), _dp(dw), _dp(dz)))
 
 	# ---- the hot path ---------------------------------------------------------------------------------------------------
@@ -221,38 +227,44 @@ class Ensemble:
 		self.last_stats = st.as_dict()
 		return self.last_stats
 
-	def integrate_jumps(self, target_time, taus, xis) -> dict:
-		if self._tape is None or self._tape[0] is not taus:
-			t = np.ascontiguousarray(taus, dtype=np.float64)
-			x = np.ascontiguousarray(xis, dtype=np.float64)
-			assert t.shape == x.shape and t.shape[0] == self.B
-			self._tape = (taus, t, x, JumpTape(_dp(t), _dp(x), t.shape[1]))
+	def set_jump_tape(self, taus, xis):
+		"""Copy a jump tape ([B][L] waiting-time values and standard-normal variates) to the device.  Always uploads — the
+		arrays are not referenced afterwards, and nothing is cached by identity; call it again after editing a tape."""
+		t = np.ascontiguousarray(taus, dtype=np.float64)
+		x = np.ascontiguousarray(xis, dtype=np.float64)
+		if t.ndim != 2 or t.shape != x.shape or t.shape[0] != self.B:
+			raise ValueError("taus and xis must both have shape [B][L]")
+		self._check(self.lib.jsde_set_jump_tape(self._h, ctypes.byref(JumpTape(_dp(t), _dp(x), t.shape[1]))))
+		self.has_tape = True
+
+	def integrate_jumps(self, target_time, taus=None, xis=None) -> dict:
+		"""`taus`/`xis` given: upload them first (set_jump_tape); omitted: continue on the tape set before."""
+		if taus is not None:
+			self.set_jump_tape(taus, xis)
 		st = Stats()
-		self._check(self.lib.jsde_integrate_jumps(self._h, float(target_time), ctypes.byref(self._tape[3]), ctypes.byref(st)))
+		self._check(self.lib.jsde_integrate_jumps(self._h, float(target_time), None, ctypes.byref(st)))
 		self.last_stats = st.as_dict()
 		return self.last_stats
 
 	def integrate_jumps_generated(self, target_time, seed, first_index=0) -> dict:
 		"""Jumps whose variates are generated on the device (counter-based, csrc/philox_jumps.h): no tape."""
 		st = Stats()
-		self.lib.jsde_integrate_jumps_generated.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_uint64, ctypes.c_int64, ctypes.c_void_p]
 		self._check(self.lib.jsde_integrate_jumps_generated(self._h, float(target_time), int(seed), int(first_index), ctypes.byref(st)))
 		self.last_stats = st.as_dict()
 		return self.last_stats
 
-	def integrate_grid(self, times, taus=None, xis=None):
-		"""States at every sample time, [n_times][B][n], from ONE launch (semantics of consecutive integrate() calls)."""
+	def integrate_grid(self, times, taus=None, xis=None, jumps=None, seed=0, first_index=0):
+		"""States at every sample time, [n_times][B][n], from ONE launch (semantics of consecutive integrate() calls).
+		Jump models: pass `taus`/`xis` (uploaded first), or `jumps="tape"` (the tape set before) or `jumps="generated"`
+		with `seed`/`first_index` (counter-based variates)."""
 		times = np.ascontiguousarray(times, dtype=np.float64)
 		out = np.zeros((times.size, self.B, self.n))
-		tape = None
 		if taus is not None:
-			if self._tape is None or self._tape[0] is not taus:
-				t = np.ascontiguousarray(taus, dtype=np.float64)
-				x = np.ascontiguousarray(xis, dtype=np.float64)
-				self._tape = (taus, t, x, JumpTape(_dp(t), _dp(x), t.shape[1]))
-			tape = ctypes.byref(self._tape[3])
+			self.set_jump_tape(taus, xis)
+			jumps = "tape"
+		mode = {None: 0, "tape": 1, "generated": 2}[jumps]
 		st = Stats()
-		self._check(self.lib.jsde_integrate_grid(self._h, _dp(times), times.size, tape, _dp(out), ctypes.byref(st)))
+		self._check(self.lib.jsde_integrate_grid_jumps(self._h, _dp(times), times.size, mode, int(seed), int(first_index), _dp(out), ctypes.byref(st)))
 		self.last_stats = st.as_dict()
 		return out
 
@@ -390,7 +402,6 @@ def generated_jump_tape(lib, seed, first_index, count, length, device=0):
 	"""(taus, xis), each [count][length]: the counter-based jump variates `integrate_jumps_generated` uses"""
 	taus = np.empty((count, length))
 	xis = np.empty((count, length))
-	lib.jsde_generated_jump_tape.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_double_p, c_double_p]
 	if lib.jsde_generated_jump_tape(device, int(seed), int(first_index), int(count), int(length), _dp(taus), _dp(xis)) != 0:
 		raise JsdeError(lib.jsde_last_error().decode())
 	return taus, xis

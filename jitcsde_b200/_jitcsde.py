@@ -358,14 +358,23 @@ class jitcsde_jump(jitcsde):
 	amp : iterable of n symbolic expressions in `y(i)`, `t` and `xi`, where `xi` is the tape's standard-normal variate
 		for this jump; evaluated on the pre-jump state and added to it (reference `:696-698`).
 	xis : optional array (L,) / (B, L) of variates; drawn from `rng.standard_normal` if omitted.
-	tape_length : L when IJI is a callable (default 1024).  Past the tape's end no further jumps happen
-		(`tape_exhausted` tells).
+	tape_length : L when IJI is a callable (default 1024).  Past the tape's end no further jumps happen: the attribute
+		`tape_exhausted` then holds the number of trajectories whose jump process stopped early and a RuntimeWarning is
+		issued (the reference draws a new waiting time after every jump and never runs out, `_jitcsde.py:698-699`); use
+		a longer tape or `IJI="generated"`.
+	jump_seed : seed of the counter-based jump variates for `IJI="generated"` (default: drawn from `rng`).
+
+	Randomness after a reset: `set_initial_value` / `reset_integrator` restart the Wiener noise from the seeds; the jump
+	process is renewed as well — a callable `IJI` is called again, variates that were not supplied explicitly (`xis=None`)
+	are redrawn from `rng`, and the generated mode takes a new seed from `rng` unless `jump_seed` was given — so repeated
+	runs on one instance are independent samples, like in the reference, where IJI and amp draw from a live generator.
+	Explicit arrays (and an explicit `jump_seed`) are replayed as given.
 	waiting_time : optional symbolic expression in `y(i)`, `t` and `tau` — the reference's state- and time-dependent
 		`IJI(time, state)` (`_jitcsde.py:682-687`), evaluated on the device when a jump is scheduled; `tau` is the
 		tape's value for that jump (e.g. unit exponentials from `IJI`, and `tau/rate(y)` here).  Default: `tau`.
 	"""
 
-	def __init__(self, IJI, amp, *args, rng=None, ito=True, xis=None, tape_length=1024, waiting_time=None, **kwargs):
+	def __init__(self, IJI, amp, *args, rng=None, ito=True, xis=None, tape_length=1024, waiting_time=None, jump_seed=None, **kwargs):
 		if not ito:
 			raise NotImplementedError("I don’t know how to convert jumpy Stratonovich SDEs to Itō SDEs – nobody does.")
 		if rng is None:
@@ -382,9 +391,17 @@ class jitcsde_jump(jitcsde):
 		self._xis_arg = xis
 		self._tape_length = tape_length
 		self._taus = self._xis = None
+		self._tape_uploaded = False
+		self._jump_seed_arg = None if jump_seed is None else int(jump_seed)
+		self._jump_seed = self._jump_seed_arg
+		self.tape_exhausted = 0  # trajectories whose tape ran out before the target time (sticky until the next reset)
+
+	@property
+	def _generated(self):
+		return isinstance(self.IJI, str) and self.IJI == "generated"
 
 	def _generated_seed(self):
-		if getattr(self, "_jump_seed", None) is None:
+		if self._jump_seed is None:
 			self._jump_seed = int(self.rng.integers(0, 2 ** 63))
 		return self._jump_seed
 
@@ -416,24 +433,72 @@ class jitcsde_jump(jitcsde):
 			raise ValueError("xis must have the same shape as the waiting times")
 		self._taus = np.ascontiguousarray(taus)
 		self._xis = np.ascontiguousarray(xis)
+		self._tape_uploaded = False
 
 	def reset_integrator(self):
-		super().reset_integrator()  # the engine restarts the tape together with the noise (jsde_set_state)
+		"""The engine rewinds every trajectory's jump counter together with the noise (jsde_set_state); the jump variates
+		are renewed unless they were given explicitly (see the class docstring)."""
+		super().reset_integrator()
+		if not hasattr(self, "_taus"):
+			return  # called from the base constructor
+		self.tape_exhausted = 0
+		if callable(self.IJI) or self._xis_arg is None:
+			self._taus = self._xis = None
+			self._tape_uploaded = False
+		self._jump_seed = self._jump_seed_arg
+
+	def _prepare_jumps(self):
+		"""-> (mode, seed): uploads the tape if it is new"""
+		if self._generated:
+			return "generated", self._generated_seed()
+		self._make_tape()
+		if not self._tape_uploaded:
+			self.SDE.set_jump_tape(self._taus, self._xis)
+			self._tape_uploaded = True
+		return "tape", 0
+
+	def _after_jumps(self, stats):
+		self.last_stats = stats
+		if stats.get("n_tape_exhausted"):
+			self.tape_exhausted += stats["n_tape_exhausted"]
+			warn(f"the jump tape (length {self._taus.shape[1]}) ran out on {stats['n_tape_exhausted']} of {self.B} trajectories before the "
+				"target time: their jump process stopped early.  Use a larger tape_length or IJI=\"generated\".", RuntimeWarning, stacklevel=3)
+		self._raise_on_failure(stats)
 
 	def integrate(self, target_time):
 		"""reference `_jitcsde.py:693-700`, all trajectories in one launch"""
 		self._initiate()
-		if isinstance(self.IJI, str) and self.IJI == "generated":
+		mode, seed = self._prepare_jumps()
+		if mode == "generated":
 			# variates generated on the device (counter-based): unit exponentials feed `waiting_time`, no tape
-			stats = self.SDE.integrate_jumps_generated(target_time, self._generated_seed(), self._first_index)
-			self.last_stats = stats
-			self._raise_on_failure(stats)
-			return self._shape_out(self.SDE.get_state())
-		self._make_tape()
-		stats = self.SDE.integrate_jumps(target_time, self._taus, self._xis)
-		self.last_stats = stats
-		self._raise_on_failure(stats)
+			stats = self.SDE.integrate_jumps_generated(target_time, seed, self._first_index)
+		else:
+			stats = self.SDE.integrate_jumps(target_time)
+		self._after_jumps(stats)
 		return self._shape_out(self.SDE.get_state())
+
+	def integrate_grid(self, times):
+		"""`[self.integrate(T) for T in times]` in one launch, jumps included (tape or generated variates)."""
+		self._initiate()
+		mode, seed = self._prepare_jumps()
+		out = self.SDE.integrate_grid(times, jumps=mode, seed=seed, first_index=self._first_index)
+		self._after_jumps(self.SDE.last_stats)
+		return out[:, 0, :] if self.B == 1 else out
+
+	def checkpoint(self):
+		"""The engine's blob (see `jitcsde.checkpoint`) followed by the jump bookkeeping a later `restore` needs: the seed of
+		the generated variates.  A tape is an input the caller supplies again (explicit arrays), exactly like
+		per-trajectory control parameters."""
+		blob = super().checkpoint()
+		seed = self._generated_seed() if self._generated else 0
+		return np.concatenate([blob, np.frombuffer(np.array([seed], dtype=np.uint64).tobytes(), dtype=np.uint8)])
+
+	def restore(self, blob):
+		blob = np.ascontiguousarray(blob, dtype=np.uint8)
+		super().restore(blob[:-8])
+		seed = int(np.frombuffer(blob[-8:].tobytes(), dtype=np.uint64)[0])
+		if self._generated:
+			self._jump_seed = seed
 
 	def check(self, fail_fast=True):
 		super().check(fail_fast)

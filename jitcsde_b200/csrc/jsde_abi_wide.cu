@@ -1,94 +1,37 @@
-// extern "C" boundary (include/jsde.h) for WIDE models (one thread block per trajectory, wide.cuh).  Same ABI as
-// jsde_abi.cu; the entry points the wide path does not implement yet (single-step surface, jumps, sampling grid,
-// pin_noise) return JSDE_E_STATE with a message instead of pretending.  Must be compiled with -fmad=false.
-#include <cuda_runtime.h>
-
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <utility>
-#include <vector>
-
-#include "../../include/jsde.h"
+// extern "C" boundary (include/jsde.h) for WIDE models (one thread block per group of trajectories, wide.cuh).  Same ABI
+// as jsde_abi.cu (shared plumbing: abi_common.cuh); the entry points the wide path does not implement (single-step
+// surface, pin_noise, the generator debug stream) return JSDE_E_STATE with a message instead of pretending.
+// Must be compiled with -fmad=false.
 #include "glibc_math.h"
 #include "wide.cuh"
-#include "kernels_common.cuh"
 
 #ifndef JSDE_MODEL_HEADER
 #error "compile with -DJSDE_MODEL_HEADER=\"model.cuh\""
 #endif
 #include JSDE_MODEL_HEADER
 
+#include "abi_common.cuh"
+
 using jsde_model::Model;
 using namespace jsde;
+using namespace jsde::abi;
 using namespace jsde::wide;
 
 static_assert(Model::WIDE, "jsde_abi_wide.cu is for wide models");
 
-namespace {
-
-thread_local std::string g_error;
-
-int fail(int code, const std::string &msg)
-{
-	g_error = msg;
-	return code;
-}
-
-#define CU(call)                                                                                          \
-	do {                                                                                                  \
-		cudaError_t err__ = (call);                                                                       \
-		if (err__ != cudaSuccess)                                                                         \
-			return fail(err__ == cudaErrorMemoryAllocation ? JSDE_E_NOMEM : JSDE_E_CUDA,                  \
-				std::string(#call) + ": " + cudaGetErrorString(err__));                                   \
-	} while (0)
-
-inline unsigned grid_for(int64_t count, int block) { return (unsigned)((count + block - 1) / block); }
-
-int unsupported(const char *what)
-{
-	return fail(JSDE_E_STATE, std::string(what) + " is not implemented for wide (block-per-trajectory) models yet");
-}
-
-}  // namespace
-
-struct jsde_handle {
-	int device = 0;
-	int64_t B = 0;
-	int D = 0;
+struct jsde_handle : HandleBase {
 	int tpb = 1;  // trajectories per thread block (wide.cuh)
-	cudaStream_t stream = nullptr;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	WideView v{};
-	Controller ctrl{};
-	double first_step = 1.0;
-	uint32_t *seeds = nullptr;
-	double *par = nullptr, *shift = nullptr;
-	double *taus = nullptr, *xis = nullptr;
-	const double *tape_src_taus = nullptr, *tape_src_xis = nullptr;
-	long long tape_len = 0;
-	std::vector<void *> allocations;
 };
 
 namespace {
 
-template <class T>
-int dev_alloc(jsde_handle *h, T **ptr, size_t count)
+int unsupported(const char *what)
 {
-	void *p = nullptr;
-	CU(cudaMalloc(&p, count * sizeof(T) > 0 ? count * sizeof(T) : 16));
-	h->allocations.push_back(p);
-	*ptr = static_cast<T *>(p);
-	return JSDE_OK;
+	return fail(JSDE_E_STATE, std::string(what) + " is not implemented for wide (block-per-trajectory) models");
 }
 
-int bind(jsde_handle *h)
-{
-	CU(cudaSetDevice(h->device));
-	return JSDE_OK;
-}
-
+// drop the noise memory, restart the generator from the stored seeds (lazily), restart jump scheduling
 int reset_integrator(jsde_handle *h)
 {
 	const int64_t B = h->B;
@@ -99,8 +42,18 @@ int reset_integrator(jsde_handle *h)
 	CU(cudaMemsetAsync(h->v.jump_set, 0, B, h->stream));
 	CU(cudaMemsetAsync(h->v.tape_pos, 0, B * sizeof(long long), h->stream));
 	k_iota_rows<<<grid_for(B * h->D, 256), 256, 0, h->stream>>>(h->v.order, B, h->D);
-	k_wide_seed<<<grid_for(B, 64), 64, 0, h->stream>>>(h->v.key, h->v.pos, h->seeds, B);
 	CU(cudaGetLastError());
+	h->seed_dirty = true;
+	return JSDE_OK;
+}
+
+int ensure_seeded(jsde_handle *h)
+{
+	if (h->seed_dirty) {
+		k_wide_seed<<<grid_for(h->B, 64), 64, 0, h->stream>>>(h->v.key, h->v.pos, h->seeds, h->B);
+		CU(cudaGetLastError());
+		h->seed_dirty = false;
+	}
 	return JSDE_OK;
 }
 
@@ -128,28 +81,6 @@ int launch_integrate(jsde_handle *h, double target_time, const double *grid_time
 	}
 }
 
-int read_totals(jsde_handle *h, jsde_stats *stats_host)
-{
-	CallTotals tot;
-	CU(cudaEventRecord(h->ev1, h->stream));
-	CU(cudaMemcpyAsync(&tot, h->v.totals, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
-	CU(cudaStreamSynchronize(h->stream));
-	if (stats_host) {
-		float ms = 0.f;
-		CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-		stats_host->accepted = tot.accepted;
-		stats_host->rejected = tot.rejected;
-		stats_host->fresh_draws = tot.fresh_draws;
-		stats_host->jumps = tot.jumps;
-		stats_host->n_min_step = tot.n_min_step;
-		stats_host->n_overflow = tot.n_overflow;
-		stats_host->max_noise_depth = tot.max_depth;
-		stats_host->kernel_launches = 1;
-		stats_host->kernel_ms = ms;
-	}
-	return JSDE_OK;
-}
-
 int choose_tpb(int device, int64_t B)
 {
 	static const int allowed[] = {1, 2, 4, 6, 7, 8};
@@ -170,31 +101,16 @@ int choose_tpb(int device, int64_t B)
 
 }  // namespace
 
+JSDE_DEFINE_COMMON_ENTRY_POINTS(Model)
+
 extern "C" {
 
-const char *jsde_last_error(void) { return g_error.c_str(); }
 const char *jsde_version(void) { return "jsde-b200 0.1 wide (sm_100a, fp64, -fmad=false)"; }
-const char *jsde_model_name(void) { return JSDE_MODEL_NAME; }
-
-int jsde_model_info(int *n, int *additive, int *n_params, int *has_jump)
-{
-	if (n) *n = Model::N;
-	if (additive) *additive = Model::ADDITIVE ? 1 : 0;
-	if (n_params) *n_params = Model::NPAR;
-	if (has_jump) *has_jump = Model::HAS_JUMP ? 1 : 0;
-	return JSDE_OK;
-}
-
 int jsde_destroy(jsde_t *h)
 {
 	if (!h)
 		return JSDE_OK;
-	cudaSetDevice(h->device);
-	if (h->stream) cudaStreamSynchronize(h->stream);
-	for (void *p : h->allocations) cudaFree(p);
-	if (h->ev0) cudaEventDestroy(h->ev0);
-	if (h->ev1) cudaEventDestroy(h->ev1);
-	if (h->stream) cudaStreamDestroy(h->stream);
+	destroy_base(h);
 	delete h;
 	return JSDE_OK;
 }
@@ -203,12 +119,9 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 {
 	if (!out || B <= 0 || noise_capacity < 0 || noise_capacity > MAX_DEPTH)
 		return fail(JSDE_E_ARG, "Wrong input.");
-	int count = 0;
-	cudaError_t err = cudaGetDeviceCount(&count);
-	if (err != cudaSuccess || count == 0)
-		return fail(JSDE_E_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(err));
-	if (device < 0 || device >= count)
-		return fail(JSDE_E_ARG, "Wrong input. (device index out of range)");
+	int rc = check_device(device);
+	if (rc) return rc;
+	cudaError_t err = cudaSuccess;
 	jsde_handle *h = new jsde_handle();
 	h->device = device;
 	h->B = B;
@@ -216,12 +129,8 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	if (h->D < 2) h->D = 2;
 	h->tpb = choose_tpb(device, B);
 	constexpr int n = Model::N;
-	int rc = bind(h);
 	auto bail = [&](int code) { jsde_destroy(h); return code; };
-	if (rc) return bail(rc);
-	if ((err = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-		(err = cudaEventCreate(&h->ev0)) != cudaSuccess || (err = cudaEventCreate(&h->ev1)) != cudaSuccess)
-		return bail(fail(JSDE_E_CUDA, cudaGetErrorString(err)));
+	if ((rc = bind(h)) || (rc = create_stream_and_events(h))) return bail(rc);
 	WideView &v = h->v;
 	v.B = B;
 	v.D = h->D;
@@ -238,9 +147,7 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	ALLOC(h->seeds, B); ALLOC(h->par, Model::NPAR > 0 ? Model::NPAR : 1); ALLOC(h->shift, n);
 #undef ALLOC
 	v.par = h->par;
-	Controller &c = h->ctrl;  // defaults of set_integration_parameters (_jitcsde.py:491-502), q = 1.5 (:564)
-	c.atol = 1e-10; c.rtol = 1e-5; c.min_step = 1e-10; c.max_step = 10.0; c.dec_thr = 1.1; c.inc_thr = 0.5;
-	c.safety = 0.9; c.max_factor = 5.0; c.min_factor = 0.2; c.shrink_exp = -1 / 1.5; c.grow_exp = -1 / (1.5 + 1);
+	default_controller(h);
 	if ((err = cudaMemsetAsync(h->seeds, 0, B * sizeof(uint32_t), h->stream)) != cudaSuccess ||
 		(err = cudaMemsetAsync(v.y, 0, (size_t)B * n * sizeof(double), h->stream)) != cudaSuccess ||
 		(err = cudaMemsetAsync(v.t, 0, B * sizeof(double), h->stream)) != cudaSuccess ||
@@ -287,22 +194,10 @@ int jsde_set_integration_parameters(jsde_t *h, const jsde_ctrl *p)
 {
 	if (!h || !p)
 		return fail(JSDE_E_ARG, "Wrong input.");
-	if (!(p->decrease_threshold >= 1.0) || !(p->increase_threshold <= 1.0) || !(p->max_factor >= 1.0) || !(p->min_factor <= 1.0) ||
-		!(p->safety_factor <= 1.0) || !(p->atol >= 0.0) || !(p->rtol >= 0.0) || !(p->q > 0.0))
-		return fail(JSDE_E_ARG, "Wrong input. (integration parameter out of range)");
-	int rc = bind(h);
+	int rc = apply_controller(h, p);
 	if (rc) return rc;
-	double first = p->first_step, min_step = p->min_step;
-	if (first > p->max_step) first = p->max_step;  // _jitcsde.py:536-541
-	if (min_step > first) min_step = first;
-	Controller &c = h->ctrl;
-	c.atol = p->atol; c.rtol = p->rtol; c.min_step = min_step; c.max_step = p->max_step;
-	c.dec_thr = p->decrease_threshold; c.inc_thr = p->increase_threshold; c.safety = p->safety_factor;
-	c.max_factor = p->max_factor; c.min_factor = p->min_factor;
-	c.shrink_exp = -1 / p->q;
-	c.grow_exp = -1 / (p->q + 1);
-	h->first_step = first;
-	k_fill<<<grid_for(h->B, 256), 256, 0, h->stream>>>(h->v.dt, first, h->B);
+	if ((rc = bind(h))) return rc;
+	k_fill<<<grid_for(h->B, 256), 256, 0, h->stream>>>(h->v.dt, h->first_step, h->B);
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(h->stream));
 	return JSDE_OK;
@@ -323,132 +218,115 @@ int jsde_set_parameters(jsde_t *h, const double *params_host, int per_trajectory
 	return JSDE_OK;
 }
 
-int jsde_integrate(jsde_t *h, double target_time, jsde_stats *stats_host)
+namespace {
+
+// jump_mode: 0 none, 1 tape (set before), 2 generated variates
+int select_jump_source(jsde_handle *h, int jump_mode, uint64_t seed, int64_t first_index)
+{
+	h->v.use_jumps = 0;
+	if (jump_mode == 0)
+		return JSDE_OK;
+	if (!Model::HAS_JUMP)
+		return fail(JSDE_E_STATE, "this model was generated without a jump amplitude");
+	if (jump_mode == 1) {
+		if (!h->tape_set)
+			return fail(JSDE_E_STATE, "no jump tape has been set (jsde_set_jump_tape)");
+		h->v.taus = h->taus;
+		h->v.xis = h->xis;
+		h->v.tape_len = h->tape_len;
+		h->v.generated_jumps = 0;
+	} else if (jump_mode == 2) {
+		if (first_index < 0)
+			return fail(JSDE_E_ARG, "Wrong input.");
+		h->v.generated_jumps = 1;
+		h->v.jump_seed = seed;
+		h->v.jump_first = first_index;
+	} else
+		return fail(JSDE_E_ARG, "Wrong input. (jump_mode)");
+	h->v.use_jumps = 1;
+	return JSDE_OK;
+}
+
+int integrate_common(jsde_handle *h, double target_time, int jump_mode, uint64_t seed, int64_t first_index, jsde_stats *stats_host)
 {
 	if (!h || !(target_time == target_time))
 		return fail(JSDE_E_ARG, "Wrong input.");
 	int rc = bind(h);
 	if (rc) return rc;
-	h->v.use_jumps = 0;
+	if ((rc = select_jump_source(h, jump_mode, seed, first_index))) return rc;
+	if ((rc = ensure_seeded(h))) return rc;
 	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
 	CU(cudaEventRecord(h->ev0, h->stream));
 	if ((rc = launch_integrate(h, target_time))) return rc;
-	return read_totals(h, stats_host);
+	return finish_call(h, h->v.totals, stats_host, 1);
 }
 
-namespace {
-int upload_tape(jsde_handle *h, const jsde_jump_tape *tape)
-{
-	if (tape->taus_host != h->tape_src_taus || tape->xis_host != h->tape_src_xis || tape->length != h->tape_len) {
-		const size_t count = (size_t)h->B * (size_t)tape->length;
-		int rc;
-		if ((rc = dev_alloc(h, &h->taus, count)) || (rc = dev_alloc(h, &h->xis, count))) return rc;
-		CU(cudaMemcpyAsync(h->taus, tape->taus_host, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-		CU(cudaMemcpyAsync(h->xis, tape->xis_host, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-		h->tape_src_taus = tape->taus_host;
-		h->tape_src_xis = tape->xis_host;
-		h->tape_len = tape->length;
-	}
-	h->v.taus = h->taus;
-	h->v.xis = h->xis;
-	h->v.tape_len = h->tape_len;
-	h->v.use_jumps = 1;
-	h->v.generated_jumps = 0;
-	return JSDE_OK;
-}
 }  // namespace
 
-// jitcsde_jump.integrate (_jitcsde.py:693-700) with the variates from a tape …
-int jsde_integrate_jumps(jsde_t *h, double target_time, const jsde_jump_tape *tape, jsde_stats *stats_host)
+int jsde_integrate(jsde_t *h, double target_time, jsde_stats *stats_host) { return integrate_common(h, target_time, 0, 0, 0, stats_host); }
+
+int jsde_set_jump_tape(jsde_t *h, const jsde_jump_tape *tape)
 {
-	if (!h || !tape || tape->length < 0 || (tape->length > 0 && (!tape->taus_host || !tape->xis_host)) || !(target_time == target_time))
+	if (!h)
 		return fail(JSDE_E_ARG, "Wrong input.");
 	if (!Model::HAS_JUMP)
 		return fail(JSDE_E_STATE, "this model was generated without a jump amplitude");
 	int rc = bind(h);
 	if (rc) return rc;
-	if ((rc = upload_tape(h, tape))) return rc;
-	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
-	CU(cudaEventRecord(h->ev0, h->stream));
-	if ((rc = launch_integrate(h, target_time))) return rc;
-	return read_totals(h, stats_host);
+	return upload_tape(h, tape);
+}
+
+// jitcsde_jump.integrate (_jitcsde.py:693-700) with the variates from a tape …
+int jsde_integrate_jumps(jsde_t *h, double target_time, const jsde_jump_tape *tape, jsde_stats *stats_host)
+{
+	if (!h)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc;
+	if (tape && (rc = jsde_set_jump_tape(h, tape))) return rc;
+	return integrate_common(h, target_time, 1, 0, 0, stats_host);
 }
 
 // … or from the counter-based generator (csrc/philox_jumps.h)
 int jsde_integrate_jumps_generated(jsde_t *h, double target_time, uint64_t seed, int64_t first_index, jsde_stats *stats_host)
 {
-	if (!h || first_index < 0 || !(target_time == target_time))
-		return fail(JSDE_E_ARG, "Wrong input.");
-	if (!Model::HAS_JUMP)
-		return fail(JSDE_E_STATE, "this model was generated without a jump amplitude");
-	int rc = bind(h);
-	if (rc) return rc;
-	h->v.use_jumps = 1;
-	h->v.generated_jumps = 1;
-	h->v.jump_seed = seed;
-	h->v.jump_first = first_index;
-	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
-	CU(cudaEventRecord(h->ev0, h->stream));
-	if ((rc = launch_integrate(h, target_time))) return rc;
-	return read_totals(h, stats_host);
-}
-
-int jsde_generated_jump_tape(int device, uint64_t seed, int64_t first_index, int64_t count, int64_t length, double *taus_host, double *xis_host)
-{
-	if (first_index < 0 || count < 0 || length < 0 || !taus_host || !xis_host)
-		return fail(JSDE_E_ARG, "Wrong input.");
-	if (count * length == 0)
-		return JSDE_OK;
-	CU(cudaSetDevice(device));
-	const size_t bytes = (size_t)count * (size_t)length * sizeof(double);
-	double *taus = nullptr, *xis = nullptr;
-	cudaError_t err = cudaMalloc(&taus, bytes);
-	if (err == cudaSuccess) err = cudaMalloc(&xis, bytes);
-	if (err == cudaSuccess) {
-		k_wide_jump_tape<<<grid_for(count * length, 256), 256>>>(seed, first_index, count, length, taus, xis);
-		err = cudaGetLastError();
-	}
-	if (err == cudaSuccess) err = cudaMemcpy(taus_host, taus, bytes, cudaMemcpyDeviceToHost);
-	if (err == cudaSuccess) err = cudaMemcpy(xis_host, xis, bytes, cudaMemcpyDeviceToHost);
-	cudaFree(taus); cudaFree(xis);
-	if (err != cudaSuccess)
-		return fail(JSDE_E_CUDA, cudaGetErrorString(err));
-	return JSDE_OK;
+	return integrate_common(h, target_time, 2, seed, first_index, stats_host);
 }
 
 // the caller's sampling loop `for time in times: integrate(time)` (examples/noisy_lorenz.py:95-96) in one launch;
 // y_host [n_times][B][n]
-int jsde_integrate_grid(jsde_t *h, const double *times_host, int64_t n_times, const jsde_jump_tape *tape, double *y_host, jsde_stats *stats_host)
+int jsde_integrate_grid_jumps(jsde_t *h, const double *times_host, int64_t n_times, int jump_mode, uint64_t seed, int64_t first_index,
+	double *y_host, jsde_stats *stats_host)
 {
 	if (!h || !times_host || n_times <= 0 || n_times > 0x7fffffff || !y_host)
 		return fail(JSDE_E_ARG, "Wrong input.");
-	if (tape && !Model::HAS_JUMP)
-		return fail(JSDE_E_STATE, "this model was generated without a jump amplitude");
 	for (int64_t j = 0; j < n_times; j++)
 		if (!(times_host[j] == times_host[j]))
 			return fail(JSDE_E_ARG, "Wrong input. (sample time is NaN)");
 	int rc = bind(h);
 	if (rc) return rc;
-	h->v.use_jumps = 0;
-	if (tape && (rc = upload_tape(h, tape))) return rc;
+	if ((rc = select_jump_source(h, jump_mode, seed, first_index))) return rc;
+	if ((rc = ensure_seeded(h))) return rc;
 	const size_t count = (size_t)n_times * (size_t)h->B * Model::N;
+	Scratch scratch;
 	double *times = nullptr, *out = nullptr;
-	CU(cudaMalloc(&times, n_times * sizeof(double)));
-	if (cudaMalloc(&out, count * sizeof(double)) != cudaSuccess) {
-		cudaFree(times);
+	CU(scratch.get(&times, n_times));
+	if (scratch.get(&out, count) != cudaSuccess)
 		return fail(JSDE_E_NOMEM, "sampling grid does not fit in device memory: n_times*B*n doubles");
-	}
-	auto cleanup = [&]() { cudaFree(times); cudaFree(out); };
-	cudaError_t err = cudaMemcpyAsync(times, times_host, n_times * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-	if (err == cudaSuccess) err = cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream);
-	if (err == cudaSuccess) err = cudaEventRecord(h->ev0, h->stream);
-	if (err != cudaSuccess) { cleanup(); return fail(JSDE_E_CUDA, cudaGetErrorString(err)); }
-	if ((rc = launch_integrate(h, times_host[n_times - 1], times, (int)n_times, out)) || (rc = read_totals(h, stats_host))) { cleanup(); return rc; }
-	err = cudaMemcpy(y_host, out, count * sizeof(double), cudaMemcpyDeviceToHost);
-	cleanup();
-	if (err != cudaSuccess)
-		return fail(JSDE_E_CUDA, cudaGetErrorString(err));
+	CU(cudaMemcpyAsync(times, times_host, n_times * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
+	CU(cudaEventRecord(h->ev0, h->stream));
+	if ((rc = launch_integrate(h, times_host[n_times - 1], times, (int)n_times, out)) || (rc = finish_call(h, h->v.totals, stats_host, 1))) return rc;
+	CU(cudaMemcpy(y_host, out, count * sizeof(double), cudaMemcpyDeviceToHost));
 	return JSDE_OK;
+}
+
+int jsde_integrate_grid(jsde_t *h, const double *times_host, int64_t n_times, const jsde_jump_tape *tape, double *y_host, jsde_stats *stats_host)
+{
+	if (!h)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc;
+	if (tape && (rc = jsde_set_jump_tape(h, tape))) return rc;
+	return jsde_integrate_grid_jumps(h, times_host, n_times, tape ? 1 : 0, 0, 0, y_host, stats_host);
 }
 
 int jsde_get_state(jsde_t *h, double *y_host, double *t_host, int32_t *status_host)
@@ -489,10 +367,10 @@ int jsde_moments(jsde_t *h, double *acc_dev, const double *shift_host)
 	else
 		CU(cudaMemsetAsync(h->shift, 0, n * sizeof(double), h->stream));
 	CU(cudaMemsetAsync(acc_dev, 0, (1 + 2 * n) * sizeof(double), h->stream));
-	const int threads = 256;
-	unsigned blocks = grid_for(h->B, threads);
-	if (blocks > 148) blocks = 148;
-	k_moments<<<blocks, threads, (threads / 32) * (1 + 2 * n) * sizeof(double), h->stream>>>(h->v.y, h->v.status, h->B, n, h->shift, acc_dev, 1, n);
+	const int threads = 128;
+	unsigned chunks = (unsigned)((h->B + 31) / 32);  // >= 32 trajectories per block: one atomic per component and 32 rows
+	if (chunks > 64) chunks = 64;
+	k_moments_wide<<<dim3(grid_for(n, threads), chunks), threads, 0, h->stream>>>(h->v.y, h->v.status, h->B, n, h->shift, acc_dev);
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(h->stream));
 	return JSDE_OK;
@@ -517,10 +395,6 @@ int jsde_accept_step(jsde_t *, const uint8_t *) { return unsupported("the single
 int jsde_apply_jump(jsde_t *, const double *) { return unsupported("apply_jump"); }
 int jsde_draw_gauss_debug(jsde_t *, double, int, double *) { return unsupported("the generator debug stream"); }
 int jsde_dump_noise(jsde_t *, int64_t, double *, int, int *) { return unsupported("dump_noise"); }
-int jsde_debug_log(int, const double *, double *, int64_t) { return unsupported("debug_log"); }
-int jsde_debug_pow(int, const double *, double, double *, int64_t) { return unsupported("debug_pow"); }
-int jsde_debug_shared_div(int, const double *, const double *, double *, unsigned char *, int64_t) { return unsupported("debug_shared_div"); }
-int jsde_debug_inline_math(int, const double *, const double *, double *, unsigned char *, double *, unsigned char *, int64_t) { return unsupported("debug_inline_math"); }
 // ---- checkpoint / restore: same contract as the lane library (include/jsde.h) ----------------------------------------
 namespace {
 struct WideCheckpointHeader {
@@ -532,7 +406,7 @@ struct WideCheckpointHeader {
 };
 constexpr uint64_t WIDE_CHECKPOINT_MAGIC = 0x4a53444557434b31ull;  // "JSDEWCK1"
 
-std::vector<std::pair<void *, size_t>> checkpoint_sections(jsde_handle *h)
+Sections checkpoint_sections(jsde_handle *h)
 {
 	const size_t B = (size_t)h->B, n = Model::N, D = (size_t)h->D;
 	WideView &v = h->v;
@@ -549,10 +423,7 @@ int64_t jsde_checkpoint_bytes(jsde_t *h)
 {
 	if (!h)
 		return fail(JSDE_E_ARG, "Wrong input.");
-	size_t total = sizeof(WideCheckpointHeader);
-	for (auto &s : checkpoint_sections(h))
-		total += s.second;
-	return (int64_t)total;
+	return (int64_t)(sizeof(WideCheckpointHeader) + sections_bytes(checkpoint_sections(h)));
 }
 
 int jsde_checkpoint_save(jsde_t *h, void *blob_host, int64_t bytes)
@@ -561,19 +432,13 @@ int jsde_checkpoint_save(jsde_t *h, void *blob_host, int64_t bytes)
 		return fail(JSDE_E_ARG, "Wrong input. (checkpoint buffer size)");
 	int rc = bind(h);
 	if (rc) return rc;
+	if ((rc = ensure_seeded(h))) return rc;
 	WideCheckpointHeader hd{};
 	hd.magic = WIDE_CHECKPOINT_MAGIC; hd.version = 1; hd.n = Model::N; hd.D = h->D; hd.npar = Model::NPAR; hd.B = h->B;
 	hd.ctrl = h->ctrl; hd.first_step = h->first_step;
 	char *out = static_cast<char *>(blob_host);
 	memcpy(out, &hd, sizeof(hd));
-	out += sizeof(hd);
-	CU(cudaStreamSynchronize(h->stream));
-	for (auto &s : checkpoint_sections(h)) {
-		CU(cudaMemcpyAsync(out, s.first, s.second, cudaMemcpyDeviceToHost, h->stream));
-		out += s.second;
-	}
-	CU(cudaStreamSynchronize(h->stream));
-	return JSDE_OK;
+	return save_sections(h, checkpoint_sections(h), out + sizeof(hd));
 }
 
 int jsde_checkpoint_restore(jsde_t *h, const void *blob_host, int64_t bytes)
@@ -583,26 +448,14 @@ int jsde_checkpoint_restore(jsde_t *h, const void *blob_host, int64_t bytes)
 	WideCheckpointHeader hd;
 	const char *in = static_cast<const char *>(blob_host);
 	memcpy(&hd, in, sizeof(hd));
-	in += sizeof(hd);
 	if (hd.magic != WIDE_CHECKPOINT_MAGIC || hd.version != 1 || hd.n != Model::N || hd.B != h->B || hd.D != h->D || hd.npar != Model::NPAR)
 		return fail(JSDE_E_ARG, "Wrong input. (checkpoint belongs to a different model or ensemble shape)");
 	int rc = bind(h);
 	if (rc) return rc;
 	h->ctrl = hd.ctrl;
 	h->first_step = hd.first_step;
-	for (auto &s : checkpoint_sections(h)) {
-		CU(cudaMemcpyAsync(s.first, in, s.second, cudaMemcpyHostToDevice, h->stream));
-		in += s.second;
-	}
-	CU(cudaStreamSynchronize(h->stream));
-	return JSDE_OK;
-}
-
-int jsde_measure_fp64_peak(int device, double *tflops)
-{
-	(void)device;
-	if (tflops) *tflops = 0.0;
-	return unsupported("measure_fp64_peak (use a lane-model library)");
+	h->seed_dirty = false;
+	return restore_sections(h, checkpoint_sections(h), in + sizeof(hd));
 }
 
 }  // extern "C"

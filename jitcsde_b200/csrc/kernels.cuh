@@ -11,7 +11,7 @@ namespace jsde {
 
 constexpr int BLOCK = 128;  // single-step kernels: one trajectory per thread
 
-// ---- shared memory of the single-step kernels: one set of generator FIFOs per warp (warp_rng.cuh) ---------------------
+// ---- shared memory of the single-step kernels: glibc's log table and a scratch list per warp (warp_rng.cuh) ------------
 constexpr int LOG_TAB_DOUBLES = 256;  // {invc, logc}[128], shared by the block
 
 template <class Model>
@@ -28,7 +28,7 @@ __device__ __forceinline__ WarpRng<Model::N> make_rng(const EnsembleView &e, int
 	}
 	__syncthreads();
 	const int warp = threadIdx.x >> 5;
-	return WarpRng<Model::N>(jsde_smem + LOG_TAB_DOUBLES + warp * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP, jsde_smem, e.mt, k - (threadIdx.x & 31), live);
+	return WarpRng<Model::N>(jsde_smem + LOG_TAB_DOUBLES + warp * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP, jsde_smem, e.mt, e.rng_ring, k - (threadIdx.x & 31), live);
 }
 
 // ---- the hot path -------------------------------------------------------------------------------------------------
@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE
 
 	if (warp >= DUO_PAIRS) {  // ---- producer warpgroup ----
 		setmaxnreg_dec<DuoConfig<N, Model::ADDITIVE>::PRODUCER_REGS>();
-		PairProducer<N> P(pair_smem, pair, e.mt);
-		P.run(e.rng_spill, e.rng_level, e.mt_chunk, e.B);
+		PairProducer<N> P(pair_smem, pair, e.mt, e.rng_ring);
+		P.run(e.rng_cons, e.rng_level, e.mt_chunk);
 		return;
 	}
 
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE
 	int grid_index = 0;
 	double cur_target = target;  // differs from `target` only in sampling-grid mode
 	double next_jump = 0.0;
-	bool jump_set = false;
+	bool jump_set = false, exhausted = false;
 	long long tape_pos = 0;
 	bool active = false, sit_out = false;
 	bool need_target = true, to_jump = false;
@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE
 				if (rej) atomicAdd(&tot->rejected, (unsigned long long)rej);
 				if (L.fresh) atomicAdd(&tot->fresh_draws, (unsigned long long)L.fresh);
 				if (jumps) atomicAdd(&tot->jumps, (unsigned long long)jumps);
+				if (Model::HAS_JUMP && exhausted) atomicAdd(&tot->tape_exhausted, 1ull);
 				if (L.status == TRAJ_MIN_STEP) atomicAdd((unsigned long long *)&tot->n_min_step, 1ull);
 				if (L.status == TRAJ_NOISE_OVERFLOW) atomicAdd((unsigned long long *)&tot->n_overflow, 1ull);
 				if (L.max_depth) atomicMax(&tot->max_depth, L.max_depth);
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE
 				L.fresh = 0;
 				L.max_depth = 0;
 				acc = rej = jumps = 0;
+				exhausted = false;
 				if (Model::HAS_JUMP && use_tape) {
 					next_jump = e.next_jump[k];
 					jump_set = e.jump_set[k] != 0;
@@ -160,6 +162,8 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE
 							wait = Model::waiting_time(L.t, L.y, jsde_jump_tau(e.jump_seed, e.jump_first + k, tape_pos), L.par);
 						else if (tape_pos < e.tape_len)
 							wait = Model::waiting_time(L.t, L.y, e.taus[(int64_t)k * e.tape_len + tape_pos], L.par);
+						else
+							exhausted = true;  // reported (jsde_stats.n_tape_exhausted): this trajectory's jump process ends here
 						next_jump = L.t + wait;
 						jump_set = true;
 					}
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(BLOCK) k_get_next_step(EnsembleView e, const d
 	const bool live = k < e.B;
 	const int64_t kk = live ? k : 0;
 	WarpRng<Model::N> rng = make_rng<Model>(e, k, live);
-	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+	rng.load(e.rng_cons, e.rng_level, e.mt_chunk, kk);
 	Lane<Model> L(e, kk, rng);
 	bool go = false;
 	if (live) {
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(BLOCK) k_get_next_step(EnsembleView e, const d
 			L.store_proposal();
 		L.store();
 	}
-	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+	rng.store(e.rng_cons, e.rng_level, e.mt_chunk, kk);
 }
 
 template <class Model>
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(BLOCK) k_get_p(EnsembleView e, double atol, do
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B)
 		return;
-	WarpRng<Model::N> rng(nullptr, nullptr, e.mt, 0, false);
+	WarpRng<Model::N> rng(nullptr, nullptr, e.mt, e.rng_ring, 0, false);
 	Lane<Model> L(e, k, rng);
 	L.load_proposal();
 	p[k] = L.error_ratio(atol, rtol);
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(BLOCK) k_accept_step(EnsembleView e, const uns
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B || (mask && !mask[k]))
 		return;
-	WarpRng<Model::N> rng(nullptr, nullptr, e.mt, 0, false);
+	WarpRng<Model::N> rng(nullptr, nullptr, e.mt, e.rng_ring, 0, false);
 	Lane<Model> L(e, k, rng);
 	L.load();
 	L.load_proposal();
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(BLOCK) k_pin_noise(EnsembleView e, unsigned nu
 	const bool live = k < e.B;
 	const int64_t kk = live ? k : 0;
 	WarpRng<Model::N> rng = make_rng<Model>(e, k, live);
-	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+	rng.load(e.rng_cons, e.rng_level, e.mt_chunk, kk);
 	Lane<Model> L(e, kk, rng);
 	if (live)
 		L.load();
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(BLOCK) k_pin_noise(EnsembleView e, unsigned nu
 	}
 	if (live)
 		L.store();
-	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+	rng.store(e.rng_cons, e.rng_level, e.mt_chunk, kk);
 }
 
 // pin_noise with caller-supplied Wiener increments: item j of trajectory k has length steps[j], DW = dw[k][j][·],
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(BLOCK) k_pin_path(EnsembleView e, unsigned num
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B)
 		return;
-	WarpRng<N> rng(nullptr, nullptr, e.mt, 0, false);
+	WarpRng<N> rng(nullptr, nullptr, e.mt, e.rng_ring, 0, false);
 	Lane<Model> L(e, k, rng);
 	L.load();
 	for (unsigned j = 0; j < number && L.status == TRAJ_OK; j++) {
@@ -349,17 +353,6 @@ __global__ void __launch_bounds__(BLOCK) k_pin_path(EnsembleView e, unsigned num
 	L.store();
 }
 
-// the counter-based jump variates as a tape: taus, xis [count][length] for trajectories first .. first+count-1
-__global__ void k_jump_tape(unsigned long long seed, long long first, long long count, long long length, double *taus, double *xis)
-{
-	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= count * length)
-		return;
-	const long long k = idx / length, j = idx - k * length;
-	taus[idx] = jsde_jump_tau(seed, first + k, j);
-	xis[idx] = jsde_jump_xi(seed, first + k, j);
-}
-
 // rk_gauss stream of every trajectory: out [B][pairs][2]
 template <class Model>
 __global__ void __launch_bounds__(BLOCK) k_draw_gauss(EnsembleView e, double scale, int pairs, double *out)
@@ -368,7 +361,7 @@ __global__ void __launch_bounds__(BLOCK) k_draw_gauss(EnsembleView e, double sca
 	const bool live = k < e.B;
 	const int64_t kk = live ? k : 0;
 	WarpRng<Model::N> rng = make_rng<Model>(e, k, live);
-	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+	rng.load(e.rng_cons, e.rng_level, e.mt_chunk, kk);
 	for (int j = 0; j < pairs; j++) {
 		rng.ensure(live, 1);
 		if (live) {
@@ -380,7 +373,7 @@ __global__ void __launch_bounds__(BLOCK) k_draw_gauss(EnsembleView e, double sca
 			out[(k * pairs + j) * 2 + 1] = x2 * f;
 		}
 	}
-	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
+	rng.store(e.rng_cons, e.rng_level, e.mt_chunk, kk);
 }
 
 }  // namespace jsde

@@ -6,6 +6,7 @@
 #include "exact_div.cuh"
 #include "glibc_math.h"
 #include "mt19937.cuh"
+#include "philox_jumps.h"
 
 namespace jsde {
 
@@ -84,6 +85,45 @@ __global__ void k_moments(const double *y, const int *status, int64_t B, int n, 
 			s += sh[w * width + f];
 		atomicAdd(&acc[f], s);
 	}
+}
+
+// The same accumulators for state vectors stored [B][n] with large n (wide models): thread = component (coalesced over
+// i), the block's share of the trajectories in a loop, one atomic per component and block — no shared memory that grows
+// with n (the kernel above needs (1+2n) doubles per warp: 128 KB at n = 1000).  grid = (ceil(n/blockDim), chunks).
+__global__ void k_moments_wide(const double *y, const int *status, int64_t B, int n, const double *shift, double *acc)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t per = (B + gridDim.y - 1) / gridDim.y;
+	const int64_t k0 = (int64_t)blockIdx.y * per, k1 = k0 + per < B ? k0 + per : B;
+	double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+	const double c = i < n ? shift[i] : 0.0;
+	for (int64_t k = k0; k < k1; k++) {
+		if (status[k] != TRAJ_OK)
+			continue;
+		cnt += 1.0;
+		if (i < n) {
+			const double d = y[k * n + i] - c;
+			s1 += d;
+			s2 += d * d;
+		}
+	}
+	if (i < n) {
+		atomicAdd(&acc[1 + i], s1);
+		atomicAdd(&acc[1 + n + i], s2);
+	}
+	if (i == 0)
+		atomicAdd(&acc[0], cnt);
+}
+
+// the counter-based jump variates as a tape: taus, xis [count][length] for trajectories first .. first+count-1
+__global__ void k_jump_tape(unsigned long long seed, long long first, long long count, long long length, double *taus, double *xis)
+{
+	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= count * length)
+		return;
+	const long long k = idx / length, j = idx - k * length;
+	taus[idx] = jsde_jump_tau(seed, first + k, j);
+	xis[idx] = jsde_jump_xi(seed, first + k, j);
 }
 
 // FP64 peak: 8 independent dependent-chains of DFMA per thread

@@ -100,7 +100,7 @@ struct TrajShared {
 	// generator), whether the step under way ends at a jump, whether a jump is due on the state P7 has just committed
 	double next_jump;
 	long long tape_pos;
-	int jump_set, to_jump, pending_jump;
+	int jump_set, to_jump, pending_jump, tape_exhausted;
 	unsigned jumps;
 };
 
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 				S.running = status == TRAJ_OK;
 				S.next_jump = 0.0;
 				S.tape_pos = 0;
-				S.jump_set = S.to_jump = S.pending_jump = 0;
+				S.jump_set = S.to_jump = S.pending_jump = S.tape_exhausted = 0;
 				S.jumps = 0;
 				if (Model::HAS_JUMP && e.use_jumps) {
 					S.next_jump = e.next_jump[b];
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			S.accept = 0;
 			S.sample_slot = -1;
 			S.jumps = 0;
-			S.pending_jump = 0;
+			S.pending_jump = S.tape_exhausted = 0;
 			S.status = TRAJ_OK;
 			S.acc = S.rej = S.fresh = 0;
 			S.max_depth = 0;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			int gi = S.grid_index, jump_set = S.jump_set;
 			long long tape_pos = S.tape_pos;
 			unsigned jumped = 0;
-			bool to_jump = false, apply = S.pending_jump != 0, still_running = true;
+			bool to_jump = false, apply = S.pending_jump != 0, still_running = true, exhausted = false;
 			double *const Ycur = e.y + b * N;
 			while (true) {
 				if (Model::HAS_JUMP && apply) {  // apply_jump(amp(time, state)) (:696-698) on the pre-jump state
@@ -333,6 +333,8 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 							wait = Model::waiting_time(t, Ycur, jsde_jump_tau(e.jump_seed, e.jump_first + b, tape_pos), e.par);
 						else if (tape_pos < e.tape_len)
 							wait = Model::waiting_time(t, Ycur, e.taus[b * e.tape_len + tape_pos], e.par);
+						else
+							exhausted = true;  // reported (jsde_stats.n_tape_exhausted): this trajectory's jump process ends here
 						next_jump = t + wait;
 						jump_set = 1;
 					}
@@ -370,6 +372,8 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 				S.to_jump = to_jump;
 				S.pending_jump = 0;
 				S.jumps += jumped;
+				if (exhausted)
+					S.tape_exhausted = 1;
 				if (!still_running)
 					S.running = 0;
 			}
@@ -761,6 +765,7 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 				e.tape_pos[b] = S.tape_pos;
 			}
 			if (S.jumps) atomicAdd(&e.totals->jumps, (unsigned long long)S.jumps);
+			if (S.tape_exhausted) atomicAdd(&e.totals->tape_exhausted, 1ull);
 			if (S.acc) atomicAdd(&e.totals->accepted, (unsigned long long)S.acc);
 			if (S.rej) atomicAdd(&e.totals->rejected, (unsigned long long)S.rej);
 			if (S.fresh) atomicAdd(&e.totals->fresh_draws, (unsigned long long)S.fresh);
@@ -769,17 +774,6 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			atomicMax(&e.totals->max_depth, S.max_depth);
 		}
 	}
-}
-
-// the counter-based jump variates as a tape: taus, xis [count][length] for trajectories first .. first+count-1
-__global__ void k_wide_jump_tape(unsigned long long seed, long long first, long long count, long long length, double *taus, double *xis)
-{
-	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= count * length)
-		return;
-	const long long k = idx / length, j = idx - k * length;
-	taus[idx] = jsde_jump_tau(seed, first + k, j);
-	xis[idx] = jsde_jump_xi(seed, first + k, j);
 }
 
 __global__ void k_iota_rows(int *order, int64_t B, int D)

@@ -34,6 +34,9 @@ OUT_DIR = os.path.join(HERE, "_ref")
 FLAGS = {
 	"strict": ["-std=c11", "-O2", "-ffp-contract=off"],
 	"default": ["-std=c11", "-Ofast", "-g0", "-march=native", "-mtune=native", "-Wno-unknown-pragmas"],
+	# the reference's omp=True path (`_jitcsde.py:331-334`: -fopenmp added to compile and link arguments): the template's
+	# `#pragma omp parallel for` loops over components become active (jitced_template.c:132-557)
+	"default_omp": ["-std=c11", "-Ofast", "-g0", "-march=native", "-mtune=native", "-fopenmp"],
 }
 
 
@@ -111,6 +114,9 @@ def build(spec, flavour: str = "strict", force: bool = False) -> str:
 			os.path.join(tmp, name + ".c"), "-o", target, "-lm",
 		]
 		res = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp)
+		if res.returncode != 0 and cmd[0] != "gcc" and shutil.which("gcc"):  # e.g. a $CC wrapper that lacks libgomp.spec
+			cmd[0] = shutil.which("gcc")
+			res = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp)
 		if res.returncode != 0:
 			raise RuntimeError("reference core failed to compile:\n" + res.stderr[-4000:])
 	with open(stamp, "w") as fh:
@@ -144,7 +150,7 @@ def available(spec, flavour: str = "strict") -> bool:
 	target = os.path.join(OUT_DIR, module_name(spec, flavour) + ".so")
 	if not os.path.isfile(target):
 		return False
-	if flavour == "default":  # built with -march=native: usable only on a CPU with the same feature set
+	if flavour.startswith("default"):  # built with -march=native: usable only on a CPU with the same feature set
 		try:
 			return open(target + ".cpu").read() == cpu_signature()
 		except OSError:

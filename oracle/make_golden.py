@@ -125,8 +125,33 @@ def jumpy(spec, B, T, tape_len):
 	return {"model": spec.name, "B": B, "T": hx(T), "tape_len": tape_len, "rows": rows}
 
 
+def long_horizon():
+	"""
+	The configured horizons ("parity at the configured horizon is untested"): whole trajectories to T = 100
+	for the additive (SRA, BASELINE.json configs[1]) and the multiplicative (SRI) Lorenz system, and configs[0] itself —
+	examples/noisy_lorenz.py: y0 = default_rng(42).random(3), 10 000 integrate() calls on arange(0, 100, 0.01) — of
+	which every 250th sample, the last one and the step counts are kept.
+	"""
+	g = {"trajectories": [trajectories(models.lorenz_additive, 8, 100.0), trajectories(models.lorenz_multiplicative, 8, 100.0)]}
+	spec = models.lorenz_multiplicative
+	mod = build_ref.load(spec, "strict")
+	y0 = np.random.default_rng(seed=42).random(3)  # examples/noisy_lorenz.py:75,91
+	times = np.arange(0.0, 100.0, 0.01)            # :95
+	R = ref_driver.RefIntegrator(mod, y0, 0.0, 42)
+	ys = np.array([R.integrate(float(T)) for T in times])
+	keep = sorted(set(range(0, len(times), 250)) | {len(times) - 1})
+	g["config1"] = {"model": spec.name, "y0": hx(y0), "seed": 42, "n_times": len(times), "kept": keep, "ys": hx(ys[keep]),
+		"accepted": R.accepted, "rejected": R.rejected, "checksum_xor": format(int(np.bitwise_xor.reduce(ys.view(np.uint64).ravel())), "016x")}
+	path = os.path.join(OUT, "reference_core_T100.json")
+	with open(path, "w") as fh:
+		json.dump(g, fh, indent=1)
+	print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
 	os.makedirs(OUT, exist_ok=True)
+	if len(sys.argv) > 1 and sys.argv[1] == "long":
+		return long_horizon()
 	g = {}
 	g["rng"] = rng_goldens()
 	lor = [1.0, 1.0, 20.0]
@@ -169,6 +194,7 @@ def main():
 	with open(path, "w") as fh:
 		json.dump(g, fh, indent=1)
 	print("wrote", path, os.path.getsize(path), "bytes")
+	long_horizon()
 
 
 if __name__ == "__main__":
