@@ -4,8 +4,8 @@ Benchmark of the hot path: accepted trajectory-steps / second (FP64).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log2-ensemble 20] [--t-end 100]
 
-Workload (BASELINE.json configs[1], SURVEY.md §8 d config 2): noisy Lorenz, additive noise g=(0.1,0.1,0.1) (SRA),
-B = 2^20 trajectories per GPU, y0_k = default_rng(42).random((B_total,3))[k], seed_k = k (global index k), one
+Headline workload (BASELINE.json configs[1], SURVEY.md §8 d config 2): noisy Lorenz, additive noise g=(0.1,0.1,0.1)
+(SRA), B = 2^20 trajectories per GPU, y0_k = default_rng(42).random((B_total,3))[k], seed_k = k (global index k), one
 `integrate(100.0)` from t=0 with the reference's default controller parameters.  One "step" = one such pass.
 
 * `value`  — Σ accepted steps ÷ device time of the integrate kernel (CUDA events on the launching stream), inputs
@@ -16,9 +16,17 @@ B = 2^20 trajectories per GPU, y0_k = default_rng(42).random((B_total,3))[k], se
 * `roofline` — the kernel is bound by the FP64 pipe, not by HBM or tensor cores: achieved = algorithmic FLOP per
              accepted step (SURVEY.md §8 d: ≈235 for SRA-Lorenz) × accepted/s; peak = a dependent-chain DFMA kernel
              measured live on this GPU (MEASURED_PEAKS.json carries no FP64 figure).  The HBM view (≈235 B/attempt
-             against MEASURED_PEAKS.json's copy bandwidth) is reported beside it.
+             against MEASURED_PEAKS.json's copy bandwidth) is reported beside it; `traffic` comes from the ncu capture
+             named in profiles/dram_bytes_per_attempt.json (refreshed whenever the kernel changes).
+* `other_configs` — one short timed pass of every other configuration BASELINE.json names (SRI-Lorenz = the physics of
+             configs[0], Duffing and GBM = configs[2], jumpy Lorenz = configs[3], the n = 1000 network = configs[4] at
+             2^11 trajectories per GPU, i.e. the 2^14 ensemble over 8 GPUs), each with its own roofline fraction and, at
+             N = 1, a bounded CPU baseline from the reference core.
+* `strong` (N > 1) — the SAME 2^20-trajectory ensemble split N ways (2^20/N per GPU, lane recycling on).
 * `cpu_baseline` / `--impl reference` — the reference's own C core (oracle/_ref, the reference's shipping flags)
-             driven by its Python controller, one process per host core, on a bounded sample of the same workload.
+             driven by its Python controller, one process per host core, on a bounded sample of the same workload;
+             `variants` adds the strict-IEEE build, the C-only controller (interpreter overhead removed) and, for the
+             n = 1000 network, the reference's OpenMP build.
 """
 
 import argparse
@@ -37,11 +45,26 @@ sys.path.insert(0, ROOT)
 FLOP_PER_ACCEPTED = 235.0   # SRA-Lorenz, one fresh draw per attempt, 1.04 attempts per accepted step
 BYTES_PER_ATTEMPT = 235.0   # generator state + one noise item streamed through HBM
 FP64_NOMINAL_TFLOPS = 37.2  # 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz
-# DRAM traffic of the integrate kernel per attempted step, from one `ncu --set full` capture of the steady state
-# (profiles/r01_duo_final_ncu_summary.txt: dram__bytes_read.sum 23.66 GB + dram__bytes_write.sum 16.46 GB for
-# 2.7335e8 attempts at B=2^18).  A full-size launch (17 s) cannot be replayed under ncu within the GPU budget, so
-# `roofline.traffic` is this per-attempt figure times the attempts of one launch.
-NCU_DRAM_BYTES_PER_ATTEMPT = (23.661648e9 + 16.464983e9) / 273349641
+
+#: the other configurations of BASELINE.json: model, log2 of the ensemble per GPU, horizon of the timed pass, and the
+#: algorithmic FLOP per ATTEMPTED step by SURVEY.md §8(d)'s formula (SRA 27n+2Ff+2Fg, SRI 80n+2Ff+4Fg, + 43n per draw)
+OTHER_CONFIGS = (
+	dict(key="sri_lorenz", model="lorenz_multiplicative", log2_B=20, T=10.0, flop_per_attempt=397.0,
+		what="configs[0] physics (examples/noisy_lorenz.py: multiplicative noise, SRI) as an ensemble"),
+	dict(key="duffing", model="duffing", log2_B=20, T=20.0, flop_per_attempt=80 * 2 + 2 * 7 + 4 * 1 + 43 * 2,
+		what="configs[2]: stochastic Duffing oscillator, multiplicative noise (SRI)"),
+	dict(key="gbm", model="gbm", log2_B=20, T=200.0, flop_per_attempt=80 + 2 * 1 + 4 * 1 + 43,
+		what="configs[2]: geometric Brownian motion, multiplicative noise (SRI)"),
+	dict(key="jumpy_lorenz", model="lorenz_jumpy", log2_B=18, T=20.0, flop_per_attempt=397.0, jumps=True,
+		what="configs[3]: examples/noisy_and_jumpy_lorenz.py physics, counter-based jump variates (no tape)"),
+	dict(key="fhn_1000", model="fhn_1000", log2_B=11, T=1.0, flop_per_attempt=1.08e6,
+		what="configs[4]: FitzHugh–Nagumo network n=1000, dense 500x500 coupling; 2^11 trajectories per GPU (2^14 over 8 GPUs)"),
+)
+
+
+def get_spec(name):
+	from jitcsde_b200 import models
+	return models.fhn_1000() if name == "fhn_1000" else models.ALL[name]
 
 
 def measured_peaks():
@@ -50,6 +73,15 @@ def measured_peaks():
 			return json.load(fh), "measured"
 	except Exception:
 		return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def ncu_traffic():
+	"""DRAM bytes per attempted step of the headline kernel from the latest committed `ncu --set full` capture."""
+	try:
+		with open(os.path.join(ROOT, "profiles", "dram_bytes_per_attempt.json")) as fh:
+			return json.load(fh)
+	except Exception:
+		return None
 
 
 class ClockSampler:
@@ -95,48 +127,75 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
+def _jump_tape_rows(first, count, length):
+	taus = np.empty((count, length))
+	xis = np.empty((count, length))
+	for j in range(count):
+		r = np.random.default_rng([42, first + j])
+		taus[j] = r.exponential(1.0, length)
+		xis[j] = r.standard_normal(length)
+	return taus, xis
+
+
 def _cpu_worker(args):
-	"""One process per core: the reference C core + its (transcribed) Python controller on `count` trajectories."""
-	core, first, count, t_end, kind, flavour = args
+	"""One process per core: `count` trajectories of `model` to `t_end`.
+	kind "reference": the reference C core + its (transcribed) Python controller; "port": C restatement, C controller."""
+	core, first, count, t_end, kind, flavour, model, jumps = args
 	try:
 		os.sched_setaffinity(0, {core})
 	except Exception:
 		pass
-	sys.path.insert(0, ROOT)
-	from jitcsde_b200 import models
-	spec = models.lorenz_additive
-	rng_rows = np.random.default_rng(42).random((first + count, 3))[first:]
+	spec = get_spec(model)
+	rng_rows = np.random.default_rng(42).random((first + count, spec.n))[first:]
 	accepted = 0
+	taus = xis = None
+	if jumps:
+		taus, xis = _jump_tape_rows(first, count, int(4 * t_end) + 32)
 	t0 = time.perf_counter()
 	if kind == "reference":
 		from oracle import build_ref, ref_driver
 		mod = build_ref.load(spec, flavour)
 		for j in range(count):
-			R = ref_driver.RefIntegrator(mod, rng_rows[j], 0.0, first + j)
+			if jumps:
+				IJI, amp = ref_driver.tape_closures(taus[j], xis[j], lambda t, y, xi: np.array([0.0, 0.0, 0.0 + abs(y[2]) * xi]))
+				R = ref_driver.RefJumpIntegrator(IJI, amp, mod, rng_rows[j], 0.0, first + j)
+			else:
+				R = ref_driver.RefIntegrator(mod, rng_rows[j], 0.0, first + j)
 			R.integrate(t_end)
 			accepted += R.accepted
 	else:
 		from oracle import port
-		res = port.run_ensemble(spec, rng_rows, np.arange(first, first + count, dtype=np.uint32), 0.0, t_end, flavour=flavour)
+		res = port.run_ensemble(spec, rng_rows, np.arange(first, first + count, dtype=np.uint32), 0.0, t_end, flavour=flavour, taus=taus, xis=xis)
 		accepted = int(res["accepted"].sum())
 	return accepted, time.perf_counter() - t0
 
 
-def cpu_reference_pass(per_core, t_end, pool, cores, kind, flavour):
+def cpu_reference_pass(per_core, t_end, pool, cores, kind, flavour, model="lorenz_additive", jumps=False):
 	"""All host cores, `per_core` trajectories each; returns (accepted, wall seconds)."""
-	jobs = [(c, c * per_core, per_core, t_end, kind, flavour) for c in range(cores)]
+	jobs = [(c, c * per_core, per_core, t_end, kind, flavour, model, jumps) for c in range(cores)]
 	t0 = time.perf_counter()
 	out = pool.map(_cpu_worker, jobs)
 	wall = time.perf_counter() - t0
 	return sum(a for a, _ in out), wall
 
 
-def cpu_kind():
-	from jitcsde_b200 import models
+def cpu_kind(model="lorenz_additive", flavour="default"):
+	"""("reference", flavour) when the reference core built from /root/reference is usable on this host, else the port."""
 	from oracle import build_ref
-	if build_ref.available(models.lorenz_additive, "default"):
-		return "reference", "default"
-	return "port", "default"
+	if build_ref.available(get_spec(model), flavour):
+		return "reference", flavour
+	return "port", flavour
+
+
+def preload_reference(model, flavour):
+	"""Load the reference core in the parent, so that the forked workers inherit it and the driver's list of loaded native
+	libraries for this arm shows oracle/_ref/...so (round-1 verdict: the forked workers were invisible to the hook)."""
+	from oracle import build_ref, port
+	spec = get_spec(model)
+	if build_ref.available(spec, flavour):
+		build_ref.load(spec, flavour)
+	else:
+		port.load(spec, flavour)
 
 
 def host_cores():
@@ -153,6 +212,7 @@ def run_reference_arm(args):
 		return
 	cores = host_cores()
 	kind, flavour = cpu_kind()
+	preload_reference("lorenz_additive", flavour)
 	per_core = args.cpu_per_core
 	ctx = mp.get_context("fork")
 	with ctx.Pool(cores) as pool:
@@ -190,7 +250,8 @@ def run_gpu_arm(args):
 	import torch
 	import torch.distributed as dist
 
-	from jitcsde_b200 import _abi, jitcsde, models
+	from jitcsde_b200 import _abi, jitcsde, models, sharding
+	from jitcsde_b200._abi import ControllerParameters, Ensemble
 
 	world = int(os.environ.get("WORLD_SIZE", "1"))
 	rank = int(os.environ.get("RANK", "0"))
@@ -206,10 +267,19 @@ def run_gpu_arm(args):
 			dist.barrier()
 		torch.cuda.synchronize()
 
+	def over_ranks(sums, maxima):
+		"""(sums added over ranks, maxima maximised over ranks)"""
+		if world == 1:
+			return list(sums), list(maxima)
+		s = torch.tensor(list(sums), dtype=torch.float64, device="cuda")
+		m = torch.tensor(list(maxima), dtype=torch.float64, device="cuda")
+		dist.all_reduce(s, op=dist.ReduceOp.SUM)
+		dist.all_reduce(m, op=dist.ReduceOp.MAX)
+		return s.tolist(), m.tolist()
+
 	B = 1 << args.log2_ensemble
 	spec = models.lorenz_additive
 	# global index k = rank*B + j decides y0 and seed, so results do not depend on the number of GPUs
-	from jitcsde_b200 import sharding
 	lo, hi = sharding.shard_range(world * B, rank, world)  # weak scaling: B per GPU
 	y0 = sharding.global_initial_states(lo, hi, 3)
 	y0_pinned = torch.from_numpy(np.ascontiguousarray(y0)).pin_memory()
@@ -240,7 +310,7 @@ def run_gpu_arm(args):
 	barrier()
 	t0 = time.perf_counter()
 	kernel_ms = 0.0
-	accepted = rejected = launches = 0
+	accepted = rejected = 0
 	for _ in range(args.steps):
 		stats, mom = one_step()
 		kernel_ms += stats["kernel_ms"]
@@ -249,27 +319,53 @@ def run_gpu_arm(args):
 	barrier()
 	wall = time.perf_counter() - t0
 	clocks = sampler.stop() if rank == 0 else None
-	# kernels launched per step: set_state (rows->cols, fill t, seed) + integrate + get_state (cols->rows) [+ moments]
+	# kernels launched per step: set_state (rows->cols, fill t) + seed + integrate + get_state (cols->rows) [+ moments]
 	launches = args.steps * (5 + (1 if world > 1 else 0))
 	failed = stats["n_min_step"] + stats["n_overflow"]
+	(accepted, rejected, failed), (kernel_ms, wall) = over_ranks([accepted, rejected, failed], [kernel_ms, wall])
+	weak_value = accepted / (kernel_ms * 1e-3)
 
-	# aggregate over ranks: totals summed, times max
-	vec = torch.tensor([accepted, rejected, kernel_ms, wall, failed], dtype=torch.float64, device="cuda")
-	if world > 1:
-		tot = vec.clone()
-		dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-		mx = vec.clone()
-		dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-		accepted, rejected, failed = int(tot[0].item()), int(tot[1].item()), int(tot[4].item())
-		kernel_ms, wall = mx[2].item(), mx[3].item()
+	# ---- the other configurations of BASELINE.json: one short timed pass each -------------------------------------------
+	others = {}
+	if not args.no_other_configs:
+		for cfg in OTHER_CONFIGS:
+			try:
+				others[cfg["key"]] = time_other_config(cfg, world, rank, local, fp64_peak, over_ranks, barrier)
+			except Exception as exc:  # a failing side pass must not lose the headline line
+				others[cfg["key"]] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+	# ---- strong scaling: the same 2^20 ensemble split over the ranks -------------------------------------------------------
+	strong = None
+	if world > 1 and not args.no_strong:
+		total = 1 << args.log2_ensemble
+		slo, shi = sharding.shard_range(total, rank, world)
+		os.environ["JSDE_RECYCLE"] = "1"  # 2^20/N trajectories are a few partial waves of resident lanes: keep the lanes busy
+		E = Ensemble(spec, shi - slo, device=local)
+		os.environ.pop("JSDE_RECYCLE", None)
+		E.set_integration_parameters(ControllerParameters())
+		best = None
+		for _ in range(2):
+			E.seed(sharding.global_seeds(slo, shi))
+			E.set_state(sharding.global_initial_states(slo, shi, 3), 0.0)
+			barrier()
+			st = E.integrate(args.t_end)
+			(acc_s,), (ms_s,) = over_ranks([st["accepted"]], [st["kernel_ms"]])
+			best = (acc_s, ms_s) if best is None or ms_s < best[1] else best
+		E.close()
+		strong_value = best[0] / (best[1] * 1e-3)
+		strong = {"ensemble_total": total, "trajectories_per_gpu": total // world, "value": strong_value, "unit": "steps/s",
+			"ms": best[1], "accepted": int(best[0]), "efficiency_vs_n1": strong_value / weak_value,
+			"note": "same 2^20-trajectory ensemble split over the ranks, lane recycling on; efficiency = value / (this run's weak-scaling "
+				"value, i.e. N x the per-GPU rate of a full 2^20 ensemble on the same GPUs)"}
 
 	if rank == 0:
 		peaks, peaks_src = measured_peaks()
-		value = accepted / (kernel_ms * 1e-3)
+		value = weak_value
 		e2e = accepted / wall
 		attempts = accepted + rejected
 		achieved_tflops = value * FLOP_PER_ACCEPTED / 1e12 / world
 		hbm_gbs = attempts / (kernel_ms * 1e-3) * BYTES_PER_ATTEMPT / 1e9 / world
+		traffic = ncu_traffic()
 		line = {
 			"metric": "accepted trajectory-steps/sec (FP64)", "value": value, "unit": "steps/s", "n_gpus": world,
 			"steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps, "higher_is_better": True,
@@ -277,37 +373,137 @@ def run_gpu_arm(args):
 			"e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": int(B * 3 * 8 + B * 4), "d2h_bytes_per_step": int(B * 3 * 8),
 				"ms_per_step": wall / args.steps * 1e3},
 			"gpu_launches": launches, "clocks": clocks,
-			"accepted_per_step": accepted // args.steps, "rejected_per_step": rejected // args.steps, "failed_trajectories": failed,
+			"accepted_per_step": int(accepted // args.steps), "rejected_per_step": int(rejected // args.steps), "failed_trajectories": int(failed),
 			"attempts_per_s": attempts / (kernel_ms * 1e-3), "accept_ratio": accepted / attempts if attempts else None,
 			"roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp64_peak,
-				"traffic": NCU_DRAM_BYTES_PER_ATTEMPT * attempts / args.steps / world,
-				"traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per attempt (B=2^18 steady-state capture, "
-					"profiles/r01_duo_final_ncu_summary.txt) x attempts of one launch; algorithmic bytes per launch = "
-					f"{BYTES_PER_ATTEMPT:g} B x attempts",
+				"traffic": traffic["dram_bytes_per_attempt"] * attempts / args.steps / world if traffic else None,
+				"traffic_source": (f"ncu dram__bytes_read.sum + dram__bytes_write.sum per attempt ({traffic['source']}) x attempts of one launch; "
+					f"algorithmic bytes per launch = {BYTES_PER_ATTEMPT:g} B x attempts") if traffic else None,
 				"per_gpu": True, "flop_per_accepted_step": FLOP_PER_ACCEPTED,
 				"peak_source": "dependent-chain DFMA kernel measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
 				"hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0),
 					"bytes_per_attempt": BYTES_PER_ATTEMPT, "peak_source": peaks_src}},
+			"other_configs": others,
 		}
+		if strong:
+			line["strong"] = strong
 		if world == 1 and not args.no_cpu_baseline:
 			line["cpu_baseline"] = cpu_baseline(args)
+			for cfg in OTHER_CONFIGS:
+				if cfg["key"] in others and "error" not in others[cfg["key"]]:
+					try:
+						others[cfg["key"]]["cpu_baseline"] = cpu_baseline_other(cfg)
+					except Exception as exc:
+						others[cfg["key"]]["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 		print(json.dumps(line), flush=True)
 	if world > 1:
 		dist.destroy_process_group()
 
 
+def time_other_config(cfg, world, rank, local, fp64_peak, over_ranks, barrier):
+	"""One timed pass (after a short untimed one that pages the library in and ramps the clocks) of another BASELINE.json
+	configuration; B trajectories per GPU, initial states and seeds by global index like the headline."""
+	from jitcsde_b200 import sharding
+	from jitcsde_b200._abi import ControllerParameters, Ensemble
+	spec = get_spec(cfg["model"])
+	B = 1 << cfg["log2_B"]
+	lo, hi = sharding.shard_range(world * B, rank, world)
+	y0 = sharding.global_initial_states(lo, hi, spec.n)
+	if cfg["model"] == "gbm":
+		y0 = np.ones_like(y0)  # SURVEY.md §8 d config 3 (i): y0 = 1
+	E = Ensemble(spec, B, device=local)
+	E.set_integration_parameters(ControllerParameters())
+
+	def go(T):
+		E.seed(sharding.global_seeds(lo, hi))
+		E.set_state(y0, 0.0)
+		barrier()
+		if cfg.get("jumps"):
+			return E.integrate_jumps_generated(T, 42, lo)
+		return E.integrate(T)
+	go(cfg["T"] / 20)
+	st = go(cfg["T"])
+	failed = st["n_min_step"] + st["n_overflow"]
+	(acc, rej, jumps, failed), (ms,) = over_ranks([st["accepted"], st["rejected"], st["jumps"], failed], [st["kernel_ms"]])
+	mom = None
+	if cfg["model"] == "fhn_1000" and world > 1:
+		# the configuration's one collective (SURVEY.md §8 e): moments of the whole 2^14 ensemble over NCCL
+		import torch
+		acc_t = torch.zeros(1 + 2 * spec.n, dtype=torch.float64, device=torch.device("cuda", local))
+		E.moments_into(acc_t.data_ptr(), np.zeros(spec.n))
+		sharding.all_reduce_sum(acc_t)
+		m = sharding.moments_from_accumulators(acc_t.cpu().numpy(), np.zeros(spec.n))
+		mom = {"count": m["count"], "mean_v0": float(m["mean"][0]), "var_v0": float(m["var"][0])}
+	E.close()
+	attempts = acc + rej
+	value = acc / (ms * 1e-3)
+	tflops = attempts / (ms * 1e-3) * cfg["flop_per_attempt"] / 1e12 / world
+	out = {"workload": cfg["what"], "model": cfg["model"], "ensemble_per_gpu": B, "ensemble_total": B * world, "t_end": cfg["T"],
+		"value": value, "unit": "steps/s", "ms": ms, "accepted": int(acc), "rejected": int(rej), "jumps": int(jumps),
+		"failed_trajectories": int(failed), "attempts_per_s": attempts / (ms * 1e-3), "accept_ratio": acc / attempts if attempts else None,
+		"roofline": {"bound": "fp64", "achieved": tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tflops / fp64_peak,
+			"flop_per_attempt": cfg["flop_per_attempt"], "per_gpu": True}}
+	if mom:
+		out["moments_all_ranks"] = mom
+	return out
+
+
 def cpu_baseline(args):
+	"""The headline workload on the host: the reported leg (reference core, reference's default flags, Python controller,
+	one process per core) and the variants BASELINE.md §3 asks for, each on a bounded sample."""
 	import multiprocessing as mp
 	cores = host_cores()
 	kind, flavour = cpu_kind()
 	per_core = args.cpu_per_core
+	preload_reference("lorenz_additive", flavour)
 	ctx = mp.get_context("fork")
+	variants = {}
 	with ctx.Pool(cores) as pool:
 		acc, wall = cpu_reference_pass(per_core, args.t_end, pool, cores, kind, flavour)
+		small = max(1, per_core // 6)
+		skind, _ = cpu_kind("lorenz_additive", "strict")
+		a, w = cpu_reference_pass(small, args.t_end, pool, cores, skind, "strict")
+		variants["strict_flags"] = {"value": a / w, "unit": "steps/s", "kind": skind, "trajectories": small * cores, "seconds": w,
+			"what": "same legs with -O2 -ffp-contract=off (the parity oracle's build)"}
+		a, w = cpu_reference_pass(max(1, per_core // 2), args.t_end, pool, cores, "port", "default")
+		variants["c_only_controller"] = {"value": a / w, "unit": "steps/s", "kind": "port", "trajectories": max(1, per_core // 2) * cores, "seconds": w,
+			"what": "C restatement of core + controller in one loop (no interpreter between steps), reference default flags"}
 	return {"value": acc / wall, "unit": "steps/s", "cores": cores, "kind": kind,
 		"sample": f"{cores * per_core} trajectories ({per_core} per core) of the same workload integrated to t={args.t_end:g}; "
 			f"{'reference C core + its Python controller, reference default flags' if kind == 'reference' else 'C restatement, C controller'}",
-		"seconds": wall}
+		"seconds": wall, "variants": variants}
+
+
+def cpu_baseline_other(cfg):
+	"""Bounded CPU leg for another configuration: the reference core where it was built here, else the port."""
+	import multiprocessing as mp
+	cores = host_cores()
+	model = cfg["model"]
+	kind, flavour = cpu_kind(model, "default")
+	preload_reference(model, flavour)
+	T = cfg["T"]
+	per_core = {"sri_lorenz": 160, "duffing": 160, "gbm": 256, "jumpy_lorenz": 48, "fhn_1000": 6}[cfg["key"]]  # ~5 s of work per core
+	ctx = mp.get_context("fork")
+	with ctx.Pool(cores) as pool:
+		acc, wall = cpu_reference_pass(per_core, T, pool, cores, kind, flavour, model, bool(cfg.get("jumps")))
+	out = {"value": acc / wall, "unit": "steps/s", "cores": cores, "kind": kind, "seconds": wall,
+		"sample": f"{cores * per_core} trajectories ({per_core} per core) to t={T:g}; "
+			f"{'reference C core + its Python controller' if kind == 'reference' else 'C restatement, C controller'}, reference default flags"}
+	if model == "fhn_1000":
+		# the reference's omp=True path: components in parallel inside ONE trajectory, all host threads
+		from oracle import build_ref, ref_driver
+		spec = get_spec(model)
+		if build_ref.available(spec, "default_omp"):
+			mod = build_ref.load(spec, "default_omp")
+			R = ref_driver.RefIntegrator(mod, np.random.default_rng(42).random(spec.n), 0.0, 0)
+			t0 = time.perf_counter()
+			R.integrate(T / 2)
+			w = time.perf_counter() - t0
+			out["openmp"] = {"value": R.accepted / w, "unit": "steps/s", "threads": cores, "trajectories": 1, "seconds": w,
+				"what": "reference built with -fopenmp (its omp=True option), one trajectory, all host threads"}
+		else:
+			out["openmp"] = {"unavailable": "no OpenMP build of the reference core for this host CPU under oracle/_ref"}
+	return out
 
 
 def main():
@@ -320,6 +516,8 @@ def main():
 	ap.add_argument("--t-end", type=float, default=100.0)
 	ap.add_argument("--cpu-per-core", type=int, default=192, help="trajectories per host core in one CPU-reference pass")
 	ap.add_argument("--no-cpu-baseline", action="store_true")
+	ap.add_argument("--no-other-configs", action="store_true")
+	ap.add_argument("--no-strong", action="store_true")
 	args = ap.parse_args()
 	if args.impl == "reference":
 		run_reference_arm(args)

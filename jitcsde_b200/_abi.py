@@ -57,7 +57,7 @@ ABI_SYMBOLS = (
 	"jsde_integrate_grid", "jsde_integrate_grid_jumps",
 	"jsde_get_state", "jsde_get_controller_state", "jsde_moments", "jsde_get_next_step", "jsde_get_p", "jsde_accept_step",
 	"jsde_apply_jump", "jsde_set_time", "jsde_draw_gauss_debug", "jsde_dump_noise", "jsde_measure_fp64_peak",
-	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_shared_div", "jsde_debug_inline_math", "jsde_pin_noise_path", "jsde_integrate_jumps_generated", "jsde_generated_jump_tape", "jsde_checkpoint_bytes", "jsde_checkpoint_save", "jsde_checkpoint_restore", "jsde_last_error", "jsde_version",
+	"jsde_debug_log", "jsde_debug_pow", "jsde_debug_exp", "jsde_debug_shared_div", "jsde_debug_inline_math", "jsde_pin_noise_path", "jsde_integrate_jumps_generated", "jsde_generated_jump_tape", "jsde_checkpoint_bytes", "jsde_checkpoint_save", "jsde_checkpoint_restore", "jsde_last_error", "jsde_version",
 )
 
 
@@ -95,6 +95,7 @@ def _declare(lib):
 	lib.jsde_measure_fp64_peak.argtypes = [ctypes.c_int, c_double_p]
 	lib.jsde_debug_log.argtypes = [ctypes.c_int, c_double_p, c_double_p, ctypes.c_int64]
 	lib.jsde_debug_pow.argtypes = [ctypes.c_int, c_double_p, ctypes.c_double, c_double_p, ctypes.c_int64]
+	lib.jsde_debug_exp.argtypes = [ctypes.c_int, c_double_p, c_double_p, ctypes.c_int64]
 	lib.jsde_debug_shared_div.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, c_u8_p, ctypes.c_int64]
 	lib.jsde_checkpoint_bytes.argtypes = [ctypes.c_void_p]
 	lib.jsde_checkpoint_bytes.restype = ctypes.c_int64
@@ -364,6 +365,14 @@ def device_log(lib, x, device=0):
 	x = np.ascontiguousarray(x, dtype=np.float64)
 	out = np.empty_like(x)
 	if lib.jsde_debug_log(device, _dp(x), _dp(out), x.size) != 0:
+		raise JsdeError(lib.jsde_last_error().decode())
+	return out
+
+
+def device_exp(lib, x, device=0):
+	x = np.ascontiguousarray(x, dtype=np.float64)
+	out = np.empty_like(x)
+	if lib.jsde_debug_exp(device, _dp(x), _dp(out), x.size) != 0:
 		raise JsdeError(lib.jsde_last_error().decode())
 	return out
 

@@ -303,6 +303,8 @@ inline int debug_unary(int device, const double *x_host, double *out_host, int64
 	CU(cudaMemcpy(x, x_host, count * sizeof(double), cudaMemcpyHostToDevice));
 	if (which == 0)
 		k_debug_log<<<grid_for(count, 256), 256>>>(x, o, count);
+	else if (which == 2)
+		k_debug_exp<<<grid_for(count, 256), 256>>>(x, o, count);
 	else
 		k_debug_pow<<<grid_for(count, 256), 256>>>(x, yexp, o, count);
 	CU(cudaGetLastError());
@@ -374,6 +376,10 @@ inline int debug_inline_math(int device, const double *a_host, const double *b_h
 	int jsde_debug_log(int device, const double *x_host, double *out_host, int64_t count)                                               \
 	{                                                                                                                                   \
 		return ::jsde::abi::debug_unary(device, x_host, out_host, count, 0, 0.0);                                                       \
+	}                                                                                                                                   \
+	int jsde_debug_exp(int device, const double *x_host, double *out_host, int64_t count)                                               \
+	{                                                                                                                                   \
+		return ::jsde::abi::debug_unary(device, x_host, out_host, count, 2, 0.0);                                                       \
 	}                                                                                                                                   \
 	int jsde_debug_pow(int device, const double *x_host, double y, double *out_host, int64_t count)                                     \
 	{                                                                                                                                   \

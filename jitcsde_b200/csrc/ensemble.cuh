@@ -15,11 +15,7 @@
 //   mt       [B][156] uint4   generator state, one contiguous 2496-byte record per trajectory (random_numbers.c:31-38);
 //                             positions of different trajectories drift apart (rejections), so records are lane-private
 //   mt_chunk [B]         next 4-word chunk to generate (the reference's `pos` / 4, running ahead by the queued pairs)
-//   rng_ring [B][3][RING], rng_cons [B], rng_level [B]   accepted polar pairs (x1, x2, r2) generated but not yet consumed: a
-//                        ring per trajectory (warp_rng.cuh: PairRing); entries rng_cons .. rng_cons + rng_level - 1 (mod
-//                        RING) are queued.  The ring is the generator's output buffer *during* a launch as well (only the
-//                        rings of the resident trajectories are hot, and they stay in L2) — nothing is copied at a
-//                        launch's end
+//   rng_spill [CAP][3][B], rng_level [B]   polar pairs generated but not yet consumed (warp_rng.cuh), kept between launches
 //   par      [P] or [P][B]    control parameters (template:34-36)
 //   status   [B]; accepted, rejected [B]
 //   jump scheduling: next_jump [B], jump_set [B], tape_pos [B], tape taus/xis [B][L]
@@ -57,9 +53,8 @@ struct EnsembleView {
 	int *q_count, *q_cursor, *q_head;
 	uint4 *mt;
 	int *mt_chunk;
-	double *rng_ring;   // [B][3][RING] queued polar pairs (x1, x2, r2), ring per trajectory (warp_rng.cuh: PairRing<N>)
-	int *rng_cons;      // [B] ring index of the oldest queued pair
-	int *rng_level;     // [B] number of queued pairs
+	double *rng_spill;  // [CAP][3][B] accepted-but-unconsumed pairs (x1, x2, r2) between kernel launches
+	int *rng_level;     // [B]
 	const double *par;
 	int64_t par_stride;  // 0: shared, B: per trajectory
 	int *status;

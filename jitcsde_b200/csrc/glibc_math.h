@@ -267,3 +267,40 @@ JSDE_FN double jsde_pow(double x, double y)
 	const jsde_pow_tables T = {JSDE_POW_INVC, JSDE_POW_LOGC, JSDE_POW_LOGCTAIL, JSDE_EXP_TAB};
 	return jsde_pow_with(x, y, T);
 }
+
+// glibc 2.39 exp(x) (sysdeps/ieee754/dbl-64/e_exp.c, the FMA variant the x86-64 ifunc selects), for |x| < 512: generated
+// drift/diffusion code that calls exp() then gives the same bits as the reference's compiled C (e.g. the diffusion
+// 5*exp(-y^2+y-1.5)+3 of the reference's own validation scenario, tests/validation.py:21-32).  Same table and polynomial
+// as the exp_inline at the end of pow above.  Outside that range (overflow/underflow handling) the caller's ordinary
+// exp() is used — tolerance parity only there.
+JSDE_FN int jsde_exp_in_range(double x)
+{
+	const uint32_t abstop = (uint32_t)(JSDE_ASU(x) >> 52) & 0x7ff;
+	return abstop - 0x3c9u < 0x408u - 0x3c9u;  // 2^-54 <= |x| < 512
+}
+
+JSDE_FN double jsde_exp_core(double x)
+{
+	const double ks = JSDE_FMA(JSDE_EXP_INVLN2N, x, JSDE_EXP_SHIFT);
+	const uint64_t ki = JSDE_ASU(ks);
+	const double kd = ks - JSDE_EXP_SHIFT;
+	const double r = JSDE_FMA(kd, JSDE_EXP_NEGLN2LON, JSDE_FMA(kd, JSDE_EXP_NEGLN2HIN, x));
+	const int idx = 2 * (int)(ki & 127);
+	const double tail = JSDE_ASD(JSDE_PTAB(JSDE_EXP_TAB, idx));
+	const uint64_t sbits = JSDE_PTAB(JSDE_EXP_TAB, idx + 1) + (ki << 45);
+	const double scale = JSDE_ASD(sbits);
+	const double r2 = r * r;
+	const double q = JSDE_FMA(JSDE_FMA(r, JSDE_EXP_C3, JSDE_EXP_C2), r2, tail + r);
+	const double tm = JSDE_FMA(JSDE_FMA(r, JSDE_EXP_C5, JSDE_EXP_C4), r2 * r2, q);
+	return JSDE_FMA(scale, tm, scale);
+}
+
+JSDE_FN double jsde_exp(double x)
+{
+	if (jsde_exp_in_range(x))
+		return jsde_exp_core(x);
+	const uint32_t abstop = (uint32_t)(JSDE_ASU(x) >> 52) & 0x7ff;
+	if (abstop < 0x3c9u)
+		return 1.0 + x;  // |x| < 2^-54 (glibc: "tiny")
+	return exp(x);
+}

@@ -41,7 +41,6 @@ int reset_integrator(jsde_handle *h)
 	CU(cudaMemsetAsync(h->v.new_y, 0, (size_t)B * Model::N * sizeof(double), h->stream));
 	CU(cudaMemsetAsync(h->v.err, 0, (size_t)B * Model::N * sizeof(double), h->stream));
 	CU(cudaMemsetAsync(h->v.rng_level, 0, B * sizeof(int), h->stream));
-	CU(cudaMemsetAsync(h->v.rng_cons, 0, B * sizeof(int), h->stream));
 	h->seed_dirty = true;
 	return JSDE_OK;
 }
@@ -98,7 +97,7 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	ALLOC(v.q, (int64_t)ring * B * noise_item_doubles(n));
 	ALLOC(v.q_count, B); ALLOC(v.q_cursor, B); ALLOC(v.q_head, B);
 	ALLOC(v.mt, B * MT_CHUNKS); ALLOC(v.mt_chunk, B);
-	ALLOC(v.rng_ring, (int64_t)PairRing<Model::N>::DOUBLES * B); ALLOC(v.rng_cons, B); ALLOC(v.rng_level, B);
+	ALLOC(v.rng_spill, (int64_t)WarpRng<Model::N>::CAP * 3 * B); ALLOC(v.rng_level, B);
 	ALLOC(v.status, B); ALLOC(v.accepted, B); ALLOC(v.rejected, B);
 	ALLOC(v.next_jump, B); ALLOC(v.jump_set, B); ALLOC(v.tape_pos, B);
 	ALLOC(v.totals, 1);
@@ -595,7 +594,7 @@ Sections checkpoint_sections(jsde_handle *h)
 		{v.y, B * n * 8}, {v.t, B * 8}, {v.dt, B * 8}, {v.new_y, B * n * 8}, {v.err, B * n * 8}, {v.new_t, B * 8},
 		{v.q, ring * B * noise_item_doubles((int)n) * 8}, {v.q_count, B * 4}, {v.q_cursor, B * 4}, {v.q_head, B * 4},
 		{v.mt, B * MT_CHUNKS * sizeof(uint4)}, {v.mt_chunk, B * 4},
-		{v.rng_ring, (size_t)PairRing<Model::N>::DOUBLES * B * 8}, {v.rng_cons, B * 4}, {v.rng_level, B * 4},
+		{v.rng_spill, (size_t)WarpRng<Model::N>::CAP * 3 * B * 8}, {v.rng_level, B * 4},
 		{v.status, B * 4}, {v.accepted, B * 8}, {v.rejected, B * 8},
 		{v.next_jump, B * 8}, {v.jump_set, B}, {v.tape_pos, B * 8},
 		{h->seeds, B * 4}, {h->par, (size_t)(Model::NPAR > 0 ? Model::NPAR : 1) * 8},
@@ -620,7 +619,7 @@ int jsde_checkpoint_save(jsde_t *h, void *blob_host, int64_t bytes)
 	if ((rc = ensure_seeded(h))) return rc;  // the blob must hold the generator state the next draw would use
 	CheckpointHeader hd{};
 	hd.magic = CHECKPOINT_MAGIC; hd.version = 2; hd.n = Model::N; hd.additive = Model::ADDITIVE; hd.D = h->D; hd.ring = h->v.Dmask + 1;
-	hd.cap = PairRing<Model::N>::RING; hd.npar = Model::NPAR; hd.B = h->B; hd.ctrl = h->ctrl; hd.first_step = h->first_step;
+	hd.cap = WarpRng<Model::N>::CAP; hd.npar = Model::NPAR; hd.B = h->B; hd.ctrl = h->ctrl; hd.first_step = h->first_step;
 	char *out = static_cast<char *>(blob_host);
 	memcpy(out, &hd, sizeof(hd));
 	return save_sections(h, checkpoint_sections(h), out + sizeof(hd));
@@ -634,7 +633,7 @@ int jsde_checkpoint_restore(jsde_t *h, const void *blob_host, int64_t bytes)
 	const char *in = static_cast<const char *>(blob_host);
 	memcpy(&hd, in, sizeof(hd));
 	if (hd.magic != CHECKPOINT_MAGIC || hd.version != 2 || hd.n != Model::N || hd.additive != (int)Model::ADDITIVE || hd.B != h->B ||
-		hd.D != h->D || hd.ring != h->v.Dmask + 1 || hd.cap != PairRing<Model::N>::RING || hd.npar != Model::NPAR)
+		hd.D != h->D || hd.ring != h->v.Dmask + 1 || hd.cap != WarpRng<Model::N>::CAP || hd.npar != Model::NPAR)
 		return fail(JSDE_E_ARG, "Wrong input. (checkpoint belongs to a different model or ensemble shape)");
 	int rc = bind(h);
 	if (rc) return rc;

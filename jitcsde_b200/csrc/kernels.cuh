@@ -11,7 +11,7 @@ namespace jsde {
 
 constexpr int BLOCK = 128;  // single-step kernels: one trajectory per thread
 
-// ---- shared memory of the single-step kernels: glibc's log table and a scratch list per warp (warp_rng.cuh) ------------
+// ---- shared memory of the single-step kernels: one set of generator FIFOs per warp (warp_rng.cuh) ---------------------
 constexpr int LOG_TAB_DOUBLES = 256;  // {invc, logc}[128], shared by the block
 
 template <class Model>
@@ -28,7 +28,7 @@ __device__ __forceinline__ WarpRng<Model::N> make_rng(const EnsembleView &e, int
 	}
 	__syncthreads();
 	const int warp = threadIdx.x >> 5;
-	return WarpRng<Model::N>(jsde_smem + LOG_TAB_DOUBLES + warp * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP, jsde_smem, e.mt, e.rng_ring, k - (threadIdx.x & 31), live);
+	return WarpRng<Model::N>(jsde_smem + LOG_TAB_DOUBLES + warp * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP, jsde_smem, e.mt, k - (threadIdx.x & 31), live);
 }
 
 // ---- the hot path -------------------------------------------------------------------------------------------------
@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE
 
 	if (warp >= DUO_PAIRS) {  // ---- producer warpgroup ----
 		setmaxnreg_dec<DuoConfig<N, Model::ADDITIVE>::PRODUCER_REGS>();
-		PairProducer<N> P(pair_smem, pair, e.mt, e.rng_ring);
-		P.run(e.rng_cons, e.rng_level, e.mt_chunk);
+		PairProducer<N> P(pair_smem, pair, e.mt);
+		P.run(e.rng_spill, e.rng_level, e.mt_chunk, e.B);
 		return;
 	}
 
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(BLOCK) k_get_next_step(EnsembleView e, const d
 	const bool live = k < e.B;
 	const int64_t kk = live ? k : 0;
 	WarpRng<Model::N> rng = make_rng<Model>(e, k, live);
-	rng.load(e.rng_cons, e.rng_level, e.mt_chunk, kk);
+	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 	Lane<Model> L(e, kk, rng);
 	bool go = false;
 	if (live) {
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(BLOCK) k_get_next_step(EnsembleView e, const d
 			L.store_proposal();
 		L.store();
 	}
-	rng.store(e.rng_cons, e.rng_level, e.mt_chunk, kk);
+	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 }
 
 template <class Model>
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(BLOCK) k_get_p(EnsembleView e, double atol, do
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B)
 		return;
-	WarpRng<Model::N> rng(nullptr, nullptr, e.mt, e.rng_ring, 0, false);
+	WarpRng<Model::N> rng(nullptr, nullptr, e.mt, 0, false);
 	Lane<Model> L(e, k, rng);
 	L.load_proposal();
 	p[k] = L.error_ratio(atol, rtol);
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(BLOCK) k_accept_step(EnsembleView e, const uns
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B || (mask && !mask[k]))
 		return;
-	WarpRng<Model::N> rng(nullptr, nullptr, e.mt, e.rng_ring, 0, false);
+	WarpRng<Model::N> rng(nullptr, nullptr, e.mt, 0, false);
 	Lane<Model> L(e, k, rng);
 	L.load();
 	L.load_proposal();
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(BLOCK) k_pin_noise(EnsembleView e, unsigned nu
 	const bool live = k < e.B;
 	const int64_t kk = live ? k : 0;
 	WarpRng<Model::N> rng = make_rng<Model>(e, k, live);
-	rng.load(e.rng_cons, e.rng_level, e.mt_chunk, kk);
+	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 	Lane<Model> L(e, kk, rng);
 	if (live)
 		L.load();
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(BLOCK) k_pin_noise(EnsembleView e, unsigned nu
 	}
 	if (live)
 		L.store();
-	rng.store(e.rng_cons, e.rng_level, e.mt_chunk, kk);
+	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 }
 
 // pin_noise with caller-supplied Wiener increments: item j of trajectory k has length steps[j], DW = dw[k][j][·],
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(BLOCK) k_pin_path(EnsembleView e, unsigned num
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B)
 		return;
-	WarpRng<N> rng(nullptr, nullptr, e.mt, e.rng_ring, 0, false);
+	WarpRng<N> rng(nullptr, nullptr, e.mt, 0, false);
 	Lane<Model> L(e, k, rng);
 	L.load();
 	for (unsigned j = 0; j < number && L.status == TRAJ_OK; j++) {
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(BLOCK) k_draw_gauss(EnsembleView e, double sca
 	const bool live = k < e.B;
 	const int64_t kk = live ? k : 0;
 	WarpRng<Model::N> rng = make_rng<Model>(e, k, live);
-	rng.load(e.rng_cons, e.rng_level, e.mt_chunk, kk);
+	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 	for (int j = 0; j < pairs; j++) {
 		rng.ensure(live, 1);
 		if (live) {
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(BLOCK) k_draw_gauss(EnsembleView e, double sca
 			out[(k * pairs + j) * 2 + 1] = x2 * f;
 		}
 	}
-	rng.store(e.rng_cons, e.rng_level, e.mt_chunk, kk);
+	rng.store(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 }
 
 }  // namespace jsde

@@ -174,6 +174,13 @@ __global__ void k_debug_inline_math(const double *a, const double *b, double *ou
 	}
 }
 
+__global__ void k_debug_exp(const double *x, double *out, int64_t count)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count)
+		out[i] = jsde_exp(x[i]);
+}
+
 __global__ void k_debug_pow(const double *x, double yexp, double *out, int64_t count)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,23 +1,24 @@
 // Warp-cooperative Gaussian source: the 32 lanes of a warp jointly advance the Mersenne Twisters of the warp's 32
-// trajectories and queue the accepted polar candidates (x1, x2, r2) per trajectory.  The stepper then consumes exactly
-// the pairs the reference's sequential stream would give (reference jitcsde/random_numbers.c:109-130 via
-// jitcsde/jitced_template.c:145-154).
+// trajectories, eight polar candidates of four trajectories per step, and queue the accepted candidates in per-lane
+// FIFOs in shared memory.  The stepper then consumes exactly the pairs the reference's sequential stream would give
+// (reference jitcsde/random_numbers.c:109-130 via jitcsde/jitced_template.c:145-154).
 //
 // Why not one generator per lane (round-1 v1, profiles/r01_v1_*): the polar method rejects 21.5 % of candidates, so
 // lanes' stream positions drift apart and (a) every 16-byte state access of a warp touches 32 different cache lines,
 // (b) a per-lane rejection loop keeps the warp busy for the unluckiest lane (measured: 16 of 32 threads active on
-// average).  Here all global accesses to the generator state are contiguous per trajectory, every candidate is computed
-// exactly once, and the expensive log/div/sqrt run later, convergent, when a lane consumes a pair.
+// average).  Here all global accesses to the generator state are 128-byte contiguous per trajectory, every candidate
+// is computed exactly once, and the expensive log/div/sqrt run later, convergent, when a lane consumes a pair.
 //
-// PairRing<N>: the queue of a trajectory is a ring of RING pairs in global memory, [3][RING] doubles (x1s, x2s, r2s),
-// addressed by (rng_cons, rng_level) — it survives between launches without any copy, and during a launch only the
-// rings of the resident trajectories are touched (they stay in L2).  Two users share it:
-//   * the fused integrate kernel (duo.cuh): a producer warp regenerates 32 chunks of ONE trajectory per service (uniform
-//     control flow, generator words staged by bulk copies) and appends the accepted pairs; it then hands every consumer
-//     lane its next pairs through a small lane-private FIFO in shared memory;
-//   * this file's WarpRng, for the single-step kernels (get_next_step, pin_noise, the generator debug stream), where the
-//     warp that consumes the pairs also produces them: eight candidates of four trajectories per step ("slot"), pops
-//     straight from the ring.  Not performance-critical.
+// This class serves the single-step kernels (get_next_step, pin_noise, the generator debug stream), where the warp
+// that consumes the pairs also produces them.  The fused integrate kernel splits the two roles between warps
+// (duo.cuh) and shares this file's vocabulary (slot layout, FIFO row stride, spill format).
+//
+// One refill step ("op"): lane l serves trajectory T = (g-th trajectory that has room, g = l/8), candidate j = l%8:
+//   loads state chunk c+j and tap chunk c+99+j of T (c = T's stream position), exchanges the two edge words with its
+//   neighbour by shuffle, writes the regenerated chunk back (mt19937.cuh explains the incremental twist), tempers,
+//   forms the candidate, and — if accepted — stores (x1, x2, r2) at T's FIFO tail + rank (rank by ballot/popc keeps
+//   stream order).  A trajectory's position always advances by 8 chunks; surplus pairs stay queued, also across
+//   kernel launches (spilled to global memory at kernel end).
 #pragma once
 
 #include "gauss.cuh"
@@ -25,68 +26,114 @@
 
 namespace jsde {
 
-constexpr int RNG_GROUP = 8;        // WarpRng: candidates per trajectory and slot
-constexpr int SERVICE_CHUNKS = 32;  // duo.cuh: chunks (= candidates) per service of one trajectory, one per lane
+constexpr int RNG_GROUP = 8;     // candidates per trajectory per op
+constexpr int RNG_STRIDE = 33;   // row stride (doubles) of the FIFO arrays: conflict-free column writes
 
-template <int N>
-struct PairRing {
-	static constexpr int L0 = 2 * N;   // duo.cuh: pairs per lane in the shared-memory FIFO (two draws)
-	static constexpr int LOW = 2 * N;  // duo.cuh: a trajectory is served when fewer pairs than this wait in its ring
-	// a service appends up to SERVICE_CHUNKS pairs while at most L0 (handed over, perhaps unread) + LOW - 1 are queued
-	static constexpr int RING = (L0 + LOW - 1 + SERVICE_CHUNKS + 1) & ~1;
-	static constexpr int DOUBLES = 3 * RING;  // per trajectory
-	static __device__ __forceinline__ int wrap(int i) { return i >= RING ? i - RING : i; }
-};
+// 16-byte asynchronous copy global -> shared (LDGSTS): no register, no scoreboard wait until cp.async.wait_group
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+	const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 
-// loads that bypass L1: ring entries are written by other lanes of the same warp / block shortly before they are read
-__device__ __forceinline__ double ld_ring(const double *p) { return __ldcg(p); }
+constexpr int RNG_STAGE_CHUNKS = 18;   // staged words of one trajectory and slot (duo.cuh): chunks c..c+8 and c+99..c+107
 
 template <int N>
 struct WarpRng {
-	using R = PairRing<N>;
-	// shared memory of one warp: order_()[32] bytes (scratch list of the lanes being served)
-	static constexpr int SMEM_DOUBLES_PER_WARP = 4;
+	// room for the pairs left over below two draws' need (2N-1) plus a full group: the producer warps of the fused
+	// integrate kernel (duo.cuh) keep every trajectory one draw ahead of its consumer; the spill format is shared
+	static constexpr int CAP = 2 * N - 1 + RNG_GROUP;
+	static constexpr int FIFO_DOUBLES = (3 * CAP * RNG_STRIDE + 1) & ~1;
+	// FIFOs | order_()[32] bytes
+	static constexpr int SMEM_DOUBLES_PER_WARP = FIFO_DOUBLES + 4;
 
-	unsigned char *order;     // this warp's scratch
+	double *fx1;              // this warp's shared memory: FIFO arrays x1, x2, r2, each [CAP][RNG_STRIDE], then ...
 	const double *log_tab;    // block-shared copy of glibc's log table {invc, logc}[128]
+	__device__ __forceinline__ double *fx2_() const { return fx1 + CAP * RNG_STRIDE; }
+	__device__ __forceinline__ double *fr2_() const { return fx1 + 2 * CAP * RNG_STRIDE; }
+	// ... order_()[32]: scratch list of lanes being served
+	__device__ __forceinline__ unsigned char *order_() const { return reinterpret_cast<unsigned char *>(fx1 + FIFO_DOUBLES); }
 	uint4 *S0;                // generator record of the warp's lane-0 trajectory
-	double *ring0;            // pair ring of the warp's lane-0 trajectory
 	int lane;
-	int cons, lvl, chunk;     // this lane's ring read index / fill level, its trajectory's next chunk
+	int rd, lvl, chunk;       // this lane's FIFO read slot / fill level, its trajectory's next chunk
 	bool usable;              // lane owns a real trajectory
 
-	__device__ __forceinline__ WarpRng(double *smem_warp, const double *shared_log_tab, uint4 *mt, double *rings, int64_t k_lane0, bool live)
-		: order(reinterpret_cast<unsigned char *>(smem_warp)), log_tab(shared_log_tab), S0(mt + k_lane0 * MT_CHUNKS),
-		  ring0(rings + k_lane0 * R::DOUBLES), lane(threadIdx.x & 31), cons(0), lvl(0), chunk(0), usable(live) {}
+	__device__ __forceinline__ WarpRng(double *smem_warp, const double *shared_log_tab, uint4 *mt, int64_t k_lane0, bool live)
+		: fx1(smem_warp), log_tab(shared_log_tab), S0(mt + k_lane0 * MT_CHUNKS), lane(threadIdx.x & 31), rd(0), lvl(0), chunk(0), usable(live) {}
 
 	// the single-step kernels never run the controller; constant-memory tables keep Lane<> instantiable with this source
 	__device__ __forceinline__ jsde_pow_tables pow_tables() const { return jsde_pow_tables{JSDE_POW_INVC, JSDE_POW_LOGC, JSDE_POW_LOGCTAIL, JSDE_EXP_TAB}; }
 
-	__device__ __forceinline__ void load(const int *cons_, const int *levels, const int *chunks, int64_t k)
+	// ---- persistence across kernel launches: spill [CAP][3][B] + level; read slot is normalised to 0 ---------------
+	__device__ __forceinline__ void load(const double *spill, const int *levels, const int *chunks, int64_t B, int64_t k)
 	{
-		cons = lvl = 0;
+		rd = 0;
+		lvl = 0;
 		if (usable) {
-			cons = cons_[k];
 			lvl = levels[k];
 			chunk = chunks[k];
+			for (int i = 0; i < lvl; i++) {
+				fx1[i * RNG_STRIDE + lane] = spill[((int64_t)i * 3 + 0) * B + k];
+				fx2_()[i * RNG_STRIDE + lane] = spill[((int64_t)i * 3 + 1) * B + k];
+				fr2_()[i * RNG_STRIDE + lane] = spill[((int64_t)i * 3 + 2) * B + k];
+			}
 		}
 		__syncwarp();
 	}
 
-	__device__ __forceinline__ void store(int *cons_, int *levels, int *chunks, int64_t k) const
+	__device__ __forceinline__ void store(double *spill, int *levels, int *chunks, int64_t B, int64_t k) const
 	{
 		__syncwarp();
 		if (usable) {
-			cons_[k] = cons;
 			levels[k] = lvl;
 			chunks[k] = chunk;
+			for (int i = 0; i < lvl; i++) {
+				int s = rd + i;
+				s = s >= CAP ? s - CAP : s;
+				spill[((int64_t)i * 3 + 0) * B + k] = fx1[s * RNG_STRIDE + lane];
+				spill[((int64_t)i * 3 + 1) * B + k] = fx2_()[s * RNG_STRIDE + lane];
+				spill[((int64_t)i * 3 + 2) * B + k] = fr2_()[s * RNG_STRIDE + lane];
+			}
 		}
 	}
 
 	// ---- cooperative refill ------------------------------------------------------------------------------------------
-	// `room` = lanes whose ring can take a full group.  They are served four at a time ("slot": 4 trajectories x 8
-	// candidates), each exactly once.  Lane (g, j) = (lane/8, lane%8) handles candidate j of the g-th trajectory of the
-	// slot: state chunk c+j and tap chunk c+99+j (mt19937.cuh), edge words from the neighbouring lane.
+	// `room` = lanes whose FIFO can take a full group.  They are served four at a time ("slot": 4 trajectories x 8
+	// candidates), each exactly once, in one run-time loop (unrolled variants blew the 32 KB instruction cache,
+	// profiles/r01_v3_*).
+	struct SlotWords {
+		uint4 a, tap;
+		uint32_t edge_next, edge_tap;
+		int T, c;
+		bool have;
+	};
+
+	__device__ __forceinline__ int served_lane(int rank) const { return order_()[rank]; }
+
+	__device__ __forceinline__ SlotWords fetch(int s, int nserved, int g, int j) const
+	{
+		SlotWords w;
+		const int rank = 4 * s + g;
+		w.have = rank < nserved;
+		w.T = w.have ? order_()[rank] : 0;
+		w.c = mt_wrap(__shfl_sync(0xffffffffu, chunk, w.T) + j);
+		w.a = make_uint4(0, 0, 0, 0);
+		w.tap = make_uint4(0, 0, 0, 0);
+		w.edge_next = 0;
+		w.edge_tap = 0;
+		if (w.have) {
+			const uint4 *ST = S0 + w.T * MT_CHUNKS;
+			w.a = ST[w.c];
+			w.tap = ST[mt_wrap(w.c + 99)];
+			if (j == RNG_GROUP - 1) {
+				w.edge_next = reinterpret_cast<const uint32_t *>(ST + mt_wrap(w.c + 1))[0];
+				w.edge_tap = reinterpret_cast<const uint32_t *>(ST + mt_wrap(w.c + 100))[0];
+			}
+		}
+		return w;
+	}
+
 	__device__ __forceinline__ void refill(unsigned room)
 	{
 		const unsigned full = 0xffffffffu;
@@ -98,57 +145,45 @@ struct WarpRng {
 		const int below = __popc(room & lt);
 		const bool mine_served = (room >> lane) & 1u;
 		if (mine_served)
-			order[below] = (unsigned char)lane;  // compacted list of the lanes to serve
+			order_()[below] = (unsigned char)lane;  // compacted list of the lanes to serve
 		__syncwarp();
 		int mine = 0;
 #pragma unroll 1
 		for (int s = 0; s < slots; s++) {
-			const int rank = 4 * s + g;
-			const bool have = rank < nserved;
-			const int T = have ? order[rank] : 0;
-			const int c = mt_wrap(__shfl_sync(full, chunk, T) + j);
-			const int tail = R::wrap(__shfl_sync(full, cons, T) + __shfl_sync(full, lvl, T));  // cons < RING, lvl <= RING - 8
-			uint4 a = make_uint4(0, 0, 0, 0), tap = make_uint4(0, 0, 0, 0);
-			uint32_t edge_next = 0, edge_tap = 0;
-			uint4 *ST = S0 + (int64_t)T * MT_CHUNKS;
-			if (have) {
-				a = ST[c];
-				tap = ST[mt_wrap(c + 99)];
-				if (j == RNG_GROUP - 1) {
-					edge_next = reinterpret_cast<const uint32_t *>(ST + mt_wrap(c + 1))[0];
-					edge_tap = reinterpret_cast<const uint32_t *>(ST + mt_wrap(c + 100))[0];
-				}
-			}
-			uint32_t next = __shfl_down_sync(full, a.x, 1);
-			uint32_t tap_hi = __shfl_down_sync(full, tap.x, 1);
+			const SlotWords w = fetch(s, nserved, g, j);
+			const int rdT = __shfl_sync(full, rd, w.T);
+			const int lvT = __shfl_sync(full, lvl, w.T);
+			uint32_t next = __shfl_down_sync(full, w.a.x, 1);
+			uint32_t tap_hi = __shfl_down_sync(full, w.tap.x, 1);
 			if (j == RNG_GROUP - 1) {
-				next = edge_next;
-				tap_hi = edge_tap;
+				next = w.edge_next;
+				tap_hi = w.edge_tap;
 			}
 			bool ok = false;
 			double x1 = 0.0, x2 = 0.0, r2 = 0.0;
-			if (have) {
+			if (w.have) {
 				uint4 r;
-				r.x = tap.y ^ mt_mix(a.x, a.y);
-				r.y = tap.z ^ mt_mix(a.y, a.z);
-				r.z = tap.w ^ mt_mix(a.z, a.w);
-				r.w = tap_hi ^ mt_mix(a.w, next);
-				ST[c] = r;
+				r.x = w.tap.y ^ mt_mix(w.a.x, w.a.y);
+				r.y = w.tap.z ^ mt_mix(w.a.y, w.a.z);
+				r.z = w.tap.w ^ mt_mix(w.a.z, w.a.w);
+				r.w = tap_hi ^ mt_mix(w.a.w, next);
+				S0[w.T * MT_CHUNKS + w.c] = r;
 				uint4 v;
-				v.x = mt_temper(a.x);
-				v.y = mt_temper(a.y);
-				v.z = mt_temper(a.z);
-				v.w = mt_temper(a.w);
+				v.x = mt_temper(w.a.x);
+				v.y = mt_temper(w.a.y);
+				v.z = mt_temper(w.a.z);
+				v.w = mt_temper(w.a.w);
 				ok = polar_candidate(v, x1, x2, r2);
 			}
 			const unsigned okm = __ballot_sync(full, ok);
 			const unsigned grp = (okm >> (g * RNG_GROUP)) & 0xffu;
 			if (ok) {
-				const int at = R::wrap(tail + __popc(grp & ((1u << j) - 1u)));
-				double *ring = ring0 + (int64_t)T * R::DOUBLES;
-				ring[at] = x1;
-				ring[R::RING + at] = x2;
-				ring[2 * R::RING + at] = r2;
+				int slot = rdT + lvT + __popc(grp & ((1u << j) - 1u));
+				slot = slot >= CAP ? slot - CAP : slot;
+				const int at = slot * RNG_STRIDE + w.T;
+				fx1[at] = x1;
+				fx2_()[at] = x2;
+				fr2_()[at] = r2;
 			}
 			// owner: the lane whose trajectory has rank r among `room` was served by slot r/4, group r%4
 			if ((below >> 2) == s)
@@ -158,11 +193,10 @@ struct WarpRng {
 			lvl += mine;
 			chunk = mt_wrap(chunk + RNG_GROUP);
 		}
-		__threadfence_block();
 		__syncwarp();
 	}
 
-	// Make sure every lane with `wants` holds at least `need` pairs (need <= 2N).  Whole warp must call (convergent).
+	// Make sure every lane with `wants` holds at least `need` pairs.  Whole warp must call (convergent).
 	// Everybody with room is served, not only the needy: every slot does useful work as long as it is full.
 	// Returns whether a refill happened (warp-uniform).
 	__device__ __forceinline__ bool ensure(bool wants, int need)
@@ -170,7 +204,7 @@ struct WarpRng {
 		const unsigned full = 0xffffffffu;
 		bool refilled = false;
 		while (__ballot_sync(full, wants && usable && lvl < need)) {
-			refill(__ballot_sync(full, wants && usable && lvl <= R::RING - RNG_GROUP));
+			refill(__ballot_sync(full, wants && usable && lvl <= CAP - RNG_GROUP));
 			refilled = true;
 		}
 		return refilled;
@@ -179,11 +213,10 @@ struct WarpRng {
 	// Pop this lane's next pair (caller guarantees lvl >= 1 via ensure()).
 	__device__ __forceinline__ void pop(double &x1, double &x2, double &r2)
 	{
-		const double *ring = ring0 + (int64_t)lane * R::DOUBLES;
-		x1 = ld_ring(ring + cons);
-		x2 = ld_ring(ring + R::RING + cons);
-		r2 = ld_ring(ring + 2 * R::RING + cons);
-		cons = R::wrap(cons + 1);
+		x1 = fx1[rd * RNG_STRIDE + lane];
+		x2 = fx2_()[rd * RNG_STRIDE + lane];
+		r2 = fr2_()[rd * RNG_STRIDE + lane];
+		rd = rd + 1 >= CAP ? 0 : rd + 1;
 		lvl--;
 	}
 };

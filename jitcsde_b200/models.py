@@ -66,6 +66,14 @@ ring6_mult = ModelSpec("ring6_mult", 6, False, tuple(f"-1.0*y({i})+0.5*(y({(i + 
 #: scalar validation SDE of `tests/validation.py:21-32` without the exponential (polynomial part only)
 cubic = ModelSpec("cubic", 1, True, ("-(y(0)*y(0)*y(0))+4*y(0)+y(0)*y(0)",), ("3.0",))
 
+#: the reference's own validation scenario in full (`tests/validation.py:21-32`): F = -y^3 + 4y + y^2,
+#: G = 5 exp(-y^2 + y - 1.5) + 3 — multiplicative noise through a transcendental function (exp is evaluated with glibc's
+#: algorithm on the device, csrc/glibc_math.h, so this model is bit-exact too)
+validation_exp = ModelSpec("validation_exp", 1, False, ("-(y(0)*y(0)*y(0))+4*y(0)+y(0)*y(0)",), ("5*exp(-(y(0)*y(0))+y(0)-1.5)+3.0",))
+
+#: noisy damped pendulum: sin/cos come from the CUDA math library on the device and from glibc in the reference's C, which
+#: differ by an ulp now and then — the TOLERANCE tier of the parity ladder (SURVEY.md §8 c rungs 2 and 4)
+pendulum = ModelSpec("pendulum", 2, False, ("y(1)", "-sin(y(0))-0.1*y(1)"), ("0.0", "0.2+0.1*cos(y(0))"))
 
 
 def fhn_network(units: int, name: str, seed: int = 7, multiplicative: bool = False, jumpy: bool = False) -> ModelSpec:
@@ -117,5 +125,5 @@ def fhn_1000() -> ModelSpec:
 
 ALL = {m.name: m for m in (
 	lorenz_additive, lorenz_additive_fixture, lorenz_multiplicative, lorenz_jumpy, lorenz_jumpy_rate,
-	gbm, gbm_pars, duffing, ou, ou_timedep, cubic, ring6, ring6_mult, fhn_small, fhn_small_mult, fhn_small_jumpy,
+	gbm, gbm_pars, duffing, ou, ou_timedep, cubic, ring6, ring6_mult, validation_exp, pendulum, fhn_small, fhn_small_mult, fhn_small_jumpy,
 )}

@@ -10,3 +10,5 @@ void restated_log_v(const double *x, double *out, size_t n) { for (size_t i = 0;
 void libm_log_v(const double *x, double *out, size_t n) { for (size_t i = 0; i < n; i++) out[i] = log(x[i]); }
 void restated_pow_v(const double *x, double y, double *out, size_t n) { for (size_t i = 0; i < n; i++) out[i] = jsde_pow(x[i], y); }
 void libm_pow_v(const double *x, double y, double *out, size_t n) { for (size_t i = 0; i < n; i++) out[i] = pow(x[i], y); }
+void restated_exp_v(const double *x, double *out, size_t n) { for (size_t i = 0; i < n; i++) out[i] = jsde_exp(x[i]); }
+void libm_exp_v(const double *x, double *out, size_t n) { for (size_t i = 0; i < n; i++) out[i] = exp(x[i]); }

@@ -276,11 +276,22 @@ def test_jump_golden():
 	assert stats["jumps"] > 0
 
 
+def test_device_exp_equals_host_libm():
+	"""exp() in generated code is glibc's algorithm on the device (csrc/glibc_math.h: jsde_exp)"""
+	import math
+	lib = _abi.load_library(models.validation_exp)
+	rng = np.random.default_rng(11)
+	for x in (rng.uniform(-5, 5, 400_000), rng.uniform(-500, 500, 300_000), rng.uniform(-1, 1, 100_000) * 2.0 ** rng.uniform(-70, -10, 100_000),
+			-(rng.uniform(-4, 4, 200_000)) ** 2 + rng.uniform(-4, 4, 200_000) - 1.5):
+		host = np.array([math.exp(v) for v in x])
+		assert_bits_equal(_abi.device_exp(lib, x), host, "exp")
+
+
 # ---- larger ensembles vs the oracle port (same seeded inputs) ----------------------------------------------------------
 @pytest.mark.parametrize("name,B,T", [
 	("lorenz_additive", 512, 1.0), ("lorenz_multiplicative", 256, 1.0), ("gbm", 512, 10.0), ("duffing", 256, 5.0),
 	("ou", 256, 5.0), ("ou_timedep", 128, 3.0), ("lorenz_additive_fixture", 128, 2.0), ("cubic", 128, 2.0),
-	("ring6", 200, 2.0), ("ring6_mult", 200, 1.0),
+	("ring6", 200, 2.0), ("ring6_mult", 200, 1.0), ("validation_exp", 256, 1.0),
 ])
 def test_ensemble_vs_oracle(name, B, T):
 	spec = models.ALL[name]

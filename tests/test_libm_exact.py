@@ -66,3 +66,18 @@ def test_pow_bit_exact(lib, y, name):
 	x = x[x > 0]
 	a, b = _run(lib, "restated_pow_v", x, y), _run(lib, "libm_pow_v", x, y)
 	assert (a.view(np.uint64) == b.view(np.uint64)).all()
+
+
+@pytest.mark.parametrize("name", ["moderate", "wide", "small", "tiny", "validation_argument"])
+def test_exp_bit_exact(lib, name):
+	"""exp() inside generated drift/diffusion code (e.g. the reference's validation scenario, tests/validation.py:21-32)"""
+	rng = np.random.default_rng(3)
+	x = {
+		"moderate": lambda: rng.uniform(-5, 5, N),
+		"wide": lambda: rng.uniform(-511.9, 511.9, N),
+		"small": lambda: rng.uniform(-1e-3, 1e-3, N),
+		"tiny": lambda: rng.uniform(-1, 1, N) * 2.0 ** rng.uniform(-80, -20, N),
+		"validation_argument": lambda: -(rng.uniform(-4, 4, N)) ** 2 + rng.uniform(-4, 4, N) - 1.5,
+	}[name]()
+	a, b = _run(lib, "restated_exp_v", x), _run(lib, "libm_exp_v", x)
+	assert (a.view(np.uint64) == b.view(np.uint64)).all()
