@@ -425,6 +425,16 @@ def time_other_config(cfg, world, rank, local, fp64_peak, over_ranks, barrier):
 	st = go(cfg["T"])
 	failed = st["n_min_step"] + st["n_overflow"]
 	(acc, rej, jumps, failed), (ms,) = over_ranks([st["accepted"], st["rejected"], st["jumps"], failed], [st["kernel_ms"]])
+	dmma = None
+	if cfg["model"] == "fhn_1000":
+		# the opt-in FP64 tensor-core coupling (tolerance-tier parity, tests/test_gpu_wide.py) next to the exact default
+		E.set_option("coupling", "dmma")
+		sd = go(cfg["T"])
+		E.set_option("coupling", "exact")
+		(acc_d, rej_d), (ms_d,) = over_ranks([sd["accepted"], sd["rejected"]], [sd["kernel_ms"]])
+		dmma = {"value": acc_d / (ms_d * 1e-3), "unit": "steps/s", "ms": ms_d, "attempts_per_s": (acc_d + rej_d) / (ms_d * 1e-3),
+			"accepted": int(acc_d), "rejected": int(rej_d),
+			"what": "same pass with coupling=dmma (mma.sync m8n8k4 f64; fused, re-associated sums: tolerance-tier parity, opt-in)"}
 	mom = None
 	if cfg["model"] == "fhn_1000" and world > 1:
 		# the configuration's one collective (SURVEY.md §8 e): moments of the whole 2^14 ensemble over NCCL
@@ -443,6 +453,9 @@ def time_other_config(cfg, world, rank, local, fp64_peak, over_ranks, barrier):
 		"failed_trajectories": int(failed), "attempts_per_s": attempts / (ms * 1e-3), "accept_ratio": acc / attempts if attempts else None,
 		"roofline": {"bound": "fp64", "achieved": tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tflops / fp64_peak,
 			"flop_per_attempt": cfg["flop_per_attempt"], "per_gpu": True}}
+	if dmma:
+		dmma["roofline_frac"] = dmma["attempts_per_s"] * cfg["flop_per_attempt"] / 1e12 / world / fp64_peak
+		out["coupling_dmma"] = dmma
 	if mom:
 		out["moments_all_ranks"] = mom
 	return out

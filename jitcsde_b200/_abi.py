@@ -52,7 +52,7 @@ class JumpTape(ctypes.Structure):
 
 #: every symbol include/jsde.h declares (tests/test_abi_symbols.py checks the built library exports them all)
 ABI_SYMBOLS = (
-	"jsde_model_info", "jsde_model_name", "jsde_create", "jsde_destroy", "jsde_set_state", "jsde_seed",
+	"jsde_model_info", "jsde_model_name", "jsde_create", "jsde_destroy", "jsde_set_option", "jsde_set_state", "jsde_seed",
 	"jsde_set_integration_parameters", "jsde_set_parameters", "jsde_pin_noise", "jsde_integrate", "jsde_set_jump_tape", "jsde_integrate_jumps",
 	"jsde_integrate_grid", "jsde_integrate_grid_jumps",
 	"jsde_get_state", "jsde_get_controller_state", "jsde_moments", "jsde_get_next_step", "jsde_get_p", "jsde_accept_step",
@@ -69,6 +69,7 @@ def _declare(lib):
 	lib.jsde_model_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 4
 	lib.jsde_create.argtypes = [ctypes.POINTER(H), ctypes.c_int, ctypes.c_int64, ctypes.c_int]
 	lib.jsde_destroy.argtypes = [H]
+	lib.jsde_set_option.argtypes = [H, ctypes.c_char_p, ctypes.c_char_p]
 	lib.jsde_set_state.argtypes = [H, c_double_p, c_double_p, ctypes.c_double]
 	lib.jsde_seed.argtypes = [H, c_u32_p]
 	lib.jsde_set_integration_parameters.argtypes = [H, ctypes.POINTER(Ctrl)]
@@ -172,6 +173,10 @@ class Ensemble:
 			self.close()
 		except Exception:
 			pass
+
+	def set_option(self, name: str, value) -> None:
+		"""`jsde_set_option`: "coupling" = "exact" | "dmma" (wide models), "recycle" = 0 | 1 (lane models)"""
+		self._check(self.lib.jsde_set_option(self._h, name.encode(), str(value).encode()))
 
 	# ---- state / seed / parameters --------------------------------------------------------------------------------
 	def set_state(self, y0, t0=0.0):

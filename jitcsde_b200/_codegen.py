@@ -133,8 +133,17 @@ def stratonovich_to_ito(f, g):
 	return [fi + gi * sympy.diff(gi, y(i)) / 2 for i, (fi, gi) in enumerate(zip(f, g))]
 
 
+def _cse_body(kind, exprs):
+	"""Common-subexpression elimination (the reference's `do_cse`, `_jitcsde.py:366-375`): temporaries first, then one
+	`set_<kind>(i, expr);` per component — the same text goes to nvcc and to the oracle's gcc, so parity is unaffected."""
+	replacements, reduced = sympy.cse(list(exprs), symbols=sympy.numbered_symbols(f"cse_{kind[0]}"), order="none")
+	lines = [f"const double {sym} = {ccode(val)};\n" for sym, val in replacements]
+	lines += [f"set_{kind}({i}, {ccode(e)});\n" for i, e in enumerate(reduced)]
+	return "".join("\t\t" + line for line in lines)
+
+
 def spec_from_symbolic(f_sym, g_sym, *, n=None, additive=None, ito=True, control_pars=(), helpers=None, g_helpers="auto",
-		jump_amp=None, jump_iji=None, name=None, simplify=None) -> ModelSpec:
+		jump_amp=None, jump_iji=None, name=None, simplify=None, do_cse=False, wide=None) -> ModelSpec:
 	f = _handle_input(f_sym)
 	g = _handle_input(g_sym)
 	if n is None:
@@ -167,9 +176,20 @@ def spec_from_symbolic(f_sym, g_sym, *, n=None, additive=None, ito=True, control
 		if len(amp) != n:
 			raise ValueError("Output of amp function has the wrong dimension")
 		jump = JumpSpec(tuple(ccode(e) for e in amp), iji="tau" if jump_iji is None else ccode(_to_sympy(jump_iji)))
+	if wide is None:
+		from ._codegen_wide import WIDE_THRESHOLD
+		wide = n > WIDE_THRESHOLD
+	if wide:
+		# large systems: one expression in the component index, evaluated by a thread block per group of trajectories
+		from ._codegen_wide import wide_spec
+		amp = None if jump_amp is None else [_to_sympy(e) for e in jump_amp]
+		return wide_spec(name, n, additive, f, g, pars, jump_amp=amp, jump_iji=None if jump_iji is None else _to_sympy(jump_iji)), f, g
 	fs = tuple(ccode(e) for e in f)
 	gs = tuple(ccode(e) for e in g)
+	f_body = _cse_body("drift", f) if do_cse else ""
+	g_body = _cse_body("diffusion", g) if do_cse else ""
 	if name is None:
 		import hashlib
-		name = "sde_" + hashlib.sha256("|".join((*fs, "#", *gs, "#", *pars, "#", *(jump.amp if jump else ()), "#", (jump.iji if jump else ""))).encode()).hexdigest()[:12]
-	return ModelSpec(name, n, bool(additive), fs, gs, control_pars=pars, jump=jump), f, g
+		name = "sde_" + hashlib.sha256("|".join((*fs, "#", *gs, "#", *pars, "#", *(jump.amp if jump else ()), "#", (jump.iji if jump else ""),
+			"#cse" if do_cse else "")).encode()).hexdigest()[:12]
+	return ModelSpec(name, n, bool(additive), fs, gs, control_pars=pars, jump=jump, f_body=f_body, g_body=g_body), f, g

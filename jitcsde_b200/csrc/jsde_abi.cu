@@ -159,6 +159,21 @@ int jsde_destroy(jsde_t *h)
 	return JSDE_OK;
 }
 
+int jsde_set_option(jsde_t *h, const char *name, const char *value)
+{
+	if (!h || !name || !value)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	if (!strcmp(name, "recycle") && (!strcmp(value, "0") || !strcmp(value, "1"))) {
+		h->recycle = value[0] == '1';
+		return JSDE_OK;
+	}
+	if (!strcmp(name, "coupling") && !strcmp(value, "exact"))
+		return JSDE_OK;
+	if (!strcmp(name, "coupling"))
+		return fail(JSDE_E_STATE, "coupling options exist for wide models with a dense coupling term only");
+	return fail(JSDE_E_ARG, std::string("Wrong input. (unknown option ") + name + "=" + value + ")");
+}
+
 int jsde_set_state(jsde_t *h, const double *y0_host, const double *t0_host, double t0)
 {
 	if (!h || !y0_host)

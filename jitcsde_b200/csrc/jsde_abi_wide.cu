@@ -147,6 +147,9 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	ALLOC(h->seeds, B); ALLOC(h->par, Model::NPAR > 0 ? Model::NPAR : 1); ALLOC(h->shift, n);
 #undef ALLOC
 	v.par = h->par;
+	v.dmma = 0;
+	if (const char *env = getenv("JSDE_WIDE_COUPLING"))  // development knob; the API is jsde_set_option
+		v.dmma = Model::UNITS > 0 && !strcmp(env, "dmma");
 	default_controller(h);
 	if ((err = cudaMemsetAsync(h->seeds, 0, B * sizeof(uint32_t), h->stream)) != cudaSuccess ||
 		(err = cudaMemsetAsync(v.y, 0, (size_t)B * n * sizeof(double), h->stream)) != cudaSuccess ||
@@ -160,6 +163,22 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 		return bail(fail(JSDE_E_CUDA, cudaGetErrorString(err)));
 	*out = h;
 	return JSDE_OK;
+}
+
+int jsde_set_option(jsde_t *h, const char *name, const char *value)
+{
+	if (!h || !name || !value)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	if (!strcmp(name, "coupling")) {
+		if (!strcmp(value, "exact")) { h->v.dmma = 0; return JSDE_OK; }
+		if (!strcmp(value, "dmma")) {
+			if (Model::UNITS <= 0)
+				return fail(JSDE_E_STATE, "this model has no dense coupling term");
+			h->v.dmma = 1;
+			return JSDE_OK;
+		}
+	}
+	return fail(JSDE_E_ARG, std::string("Wrong input. (unknown option ") + name + "=" + value + ")");
 }
 
 int jsde_set_state(jsde_t *h, const double *y0_host, const double *t0_host, double t0)

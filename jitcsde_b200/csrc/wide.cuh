@@ -70,6 +70,8 @@ struct WideView {
 	int use_jumps, generated_jumps;
 	unsigned long long jump_seed;
 	long long jump_first;
+	// opt-in: the coupling sums as FP64 tensor-core products (coupling_phase_dmma) instead of the exact register tile
+	int dmma;
 };
 
 __global__ void k_wide_seed(uint32_t *key, int *pos, const uint32_t *seeds, int64_t B)
@@ -181,6 +183,71 @@ __device__ __forceinline__ void coupling_phase(const double *__restrict__ AT, do
 #pragma unroll
 			for (int tr = 0; tr < T; tr++)
 				SC[i * TPAD + tr] = acc[q][tr];
+		}
+	}
+	__syncthreads();
+}
+
+// ---- opt-in: the same sums on the FP64 tensor cores ("coupling = dmma") --------------------------------------------------
+// c_i = sum_j A_ij (y_j - y_i) = (A V)_i - y_i * rowsum_i(A), with V = [y of the block's live trajectories | 0 ... | 1]:
+// the product's last column is the row sum.  One warp-wide  mma.sync.aligned.m8n8k4.f64  multiplies an 8x4 tile of A
+// (rows i, columns j) with a 4x8 tile of V (rows j, one column per trajectory) — 1 load of A per thread and 256 fused
+// multiply-adds per instruction, where the exact path issues 3 x T unfused FP64 instructions per loaded A_ij.  The k-sum is
+// fused and associated the hardware's way, so results differ from the reference's separately rounded loop in the last bits:
+// this path is validated at BASELINE.json's TOLERANCE tier (1e-9 relative per trajectory where the step sequence matches,
+// moments within 3 standard errors; tests/test_gpu_wide.py) and is never the default.  Needs a free column: active <= 7.
+__device__ __forceinline__ void dmma_m8n8k4(double (&d)[2], double a, double b)
+{
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+template <int UNITS>
+__device__ __forceinline__ void coupling_phase_dmma(const double *__restrict__ AT, double *SC, int tid, int active)
+{
+	constexpr int ROW_TILES = (UNITS + 7) / 8;
+	constexpr int TPW = (ROW_TILES + WWARPS - 1) / WWARPS;  // row tiles per warp
+	constexpr int ONES = TPAD - 1;                           // the column that yields the row sums
+	const int lane = tid & 31, warp = tid >> 5;
+	const int g = lane >> 2, q = lane & 3;  // fragment coordinates: A[g][q], B[q][g], D[g][2q], D[g][2q+1]
+	for (int j = tid; j < UNITS; j += WBLOCK)
+		SC[j * TPAD + ONES] = 1.0;
+	__syncthreads();
+	double acc[TPW][2];
+#pragma unroll
+	for (int m = 0; m < TPW; m++)
+		acc[m][0] = acc[m][1] = 0.0;
+#pragma unroll 2
+	for (int k0 = 0; k0 < UNITS; k0 += 4) {
+		const int j = k0 + q;
+		const bool jin = j < UNITS;
+		const double b = jin ? SC[j * TPAD + g] : 0.0;
+		const double *Aj = AT + (size_t)(jin ? j : 0) * UNITS;
+#pragma unroll
+		for (int m = 0; m < TPW; m++) {
+			const int i = (warp + m * WWARPS) * 8 + g;
+			const double a = (jin && i < UNITS) ? __ldg(Aj + i) : 0.0;
+			dmma_m8n8k4(acc[m], a, b);
+		}
+	}
+	double yi[TPW][2];
+#pragma unroll
+	for (int m = 0; m < TPW; m++) {
+		const int i = (warp + m * WWARPS) * 8 + g;
+		yi[m][0] = i < UNITS ? SC[i * TPAD + 2 * q] : 0.0;
+		yi[m][1] = i < UNITS ? SC[i * TPAD + 2 * q + 1] : 0.0;
+	}
+	__syncthreads();  // everybody has read the last y_j
+#pragma unroll
+	for (int m = 0; m < TPW; m++) {
+		const int i = (warp + m * WWARPS) * 8 + g;
+		const double rowsum = __shfl_sync(0xffffffffu, acc[m][1], (lane & ~3) | 3);  // D[g][7]
+		if (i < UNITS) {
+			if (2 * q < active)
+				SC[i * TPAD + 2 * q] = acc[m][0] - yi[m][0] * rowsum;
+			if (2 * q + 1 < active)
+				SC[i * TPAD + 2 * q + 1] = acc[m][1] - yi[m][1] * rowsum;
+			if (q == 3)
+				SC[i * TPAD + ONES] = 0.0;  // columns of absent trajectories stay zero
 		}
 	}
 	__syncthreads();
@@ -529,8 +596,12 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 		}
 
 		for (int stage = 0; stage < 2; stage++) {
-			if (UNITS > 0)
-				coupling_dispatch<T, UNITS>(active, Model::coupling_table(), SC, tid);
+			if (UNITS > 0) {
+				if (e.dmma && active < TPAD)
+					coupling_phase_dmma<(UNITS > 0 ? UNITS : 8)>(Model::coupling_table(), SC, tid, active);
+				else
+					coupling_dispatch<T, UNITS>(active, Model::coupling_table(), SC, tid);
+			}
 			if (stage == 0) {
 				// ---- P3: first stage (template:468-481) ----------------------------------------------------------------
 				int col = 0;

@@ -107,3 +107,70 @@ def test_jump_waiting_time_expression_is_printed_into_the_spec():
 	SDE.check()
 	plain = jitcsde_jump(np.ones(4), [0, 0, abs(y(2)) * xi], f, g, verbose=False)
 	assert plain.spec.jump.iji == "tau" and plain.spec.name != SDE.spec.name
+
+
+# ---- compile_C options and large symbolic systems -------------------------------------------------------------------
+def test_cse_emits_temporaries_and_keeps_the_values():
+	"""do_cse (reference `_jitcsde.py:366-375`): same drift, shared subexpressions computed once; the oracle compiles the
+	same body, so parity tests see no difference between the two sides."""
+	from oracle import port
+	fs = [sympy.sin(y(0) * y(1)) + y(0) * y(1), sympy.cos(y(0) * y(1)) - y(1)]
+	gs = [0.1 * y(0) * y(1), 0.2]
+	plain, _, _ = spec_from_symbolic(fs, gs, name="cse_plain")
+	cse, _, _ = spec_from_symbolic(fs, gs, name="cse_on", do_cse=True)
+	assert "const double cse_d0" in cse.f_body and cse.f_body.count("y(0)*y(1)") <= 1 and plain.f_body == ""
+	y0 = np.array([0.3, -0.7])
+	a = port.PortCore(plain, y0, 0.0, 5).integrate(0.2)
+	b = port.PortCore(cse, y0, 0.0, 5).integrate(0.2)
+	np.testing.assert_allclose(a, b, rtol=1e-11)
+
+
+def test_compile_options_are_honoured_or_refused():
+	S = jitcsde([sympy.sin(y(0)) ** 2 + sympy.cos(y(0)) ** 2 - y(0)], [0.1], verbose=False)
+	before = S.spec.f
+	S._library = None
+	S.spec, S.f_sym, S.g_sym = S._make_spec(simplify=True)
+	assert S.spec.f != before and "sin" not in S.spec.f[0]  # sin^2 + cos^2 -> 1
+	from jitcsde_b200 import models
+	T = jitcsde(spec=models.ou, verbose=False)
+	with pytest.raises(NotImplementedError, match="symbolic input"):
+		T.compile_C(do_cse=True)
+	with pytest.raises(NotImplementedError, match="numpy_rng"):
+		T.compile_C(numpy_rng=True)
+
+
+def symbolic_network(units, seed=7):
+	"""the FitzHugh–Nagumo network of models.fhn_network written the way a user of the reference would: Python loops"""
+	A = np.random.default_rng(seed).random((units, units))
+	fs = [y(i) - y(i) ** 3 / 3 - y(units + i) + 0.5 + sum(float(A[i, j]) / units * (y(j) - y(i)) for j in range(units)) for i in range(units)]
+	fs += [0.08 * (y(i) + 0.7 - 0.8 * y(units + i)) for i in range(units)]
+	gs = [sympy.Float(0.05)] * units + [sympy.Float(0.0)] * units
+	return fs, gs
+
+
+def test_large_symbolic_systems_become_wide_models():
+	"""n above the lane kernels' range: the dense linear coupling is recognised and the components fold into two templates"""
+	from oracle import port
+	units = 40
+	fs, gs = symbolic_network(units)
+	spec, fsym, _ = spec_from_symbolic(fs, gs)
+	assert spec.wide and spec.coupling_units == units and spec.additive and spec.n == 2 * units
+	assert spec.f_component.count("?") == 1 and "coupling" in spec.f_component  # v-template : w-template
+	# the generated code evaluates the user's drift: one tiny noise-free step through the oracle's build of the same strings
+	y0 = np.random.default_rng(1).random(spec.n)
+	P = port.PortCore(spec, y0, 0.0, 3)
+	h = 1e-7
+	P.pin_path([h], np.zeros((1, spec.n)), np.zeros((1, spec.n)))
+	P.get_next_step(h)
+	P.accept_step()
+	Yb = sympy.IndexedBase("Y")
+	drift = sympy.lambdify(Yb, [e.subs({y(k): Yb[k] for k in range(spec.n)}) for e in fsym], "numpy")
+	np.testing.assert_allclose((P.get_state() - y0) / h, np.array(drift(y0)), rtol=0, atol=1e-5)
+
+
+def test_irregular_large_systems_are_refused_with_a_reason():
+	n = 80
+	rng = np.random.default_rng(0)
+	fs = [-(1.0 + float(rng.random())) * y(i) ** (2 + i % 3) - float(rng.random()) * y((i * 7 + 3) % n) ** 2 for i in range(n)]
+	with pytest.raises(NotImplementedError, match="structural templates"):
+		spec_from_symbolic(fs, [0.1] * n)

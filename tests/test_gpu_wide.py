@@ -173,3 +173,85 @@ def test_wide_moments():
 	assert got[0] == 64
 	np.testing.assert_allclose(got[1:1 + spec.n], y.sum(axis=0), rtol=1e-12)
 	np.testing.assert_allclose(got[1 + spec.n:], (y ** 2).sum(axis=0), rtol=1e-12)
+
+
+def test_symbolic_network_through_the_front_end():
+	"""a user's Python-loop network (n = 96) goes through the symbolic front end onto the wide path; bit-identical to the
+	oracle's build of the same generated expressions, and statistically the same SDE as the hand-written model"""
+	import sympy
+	from jitcsde_b200 import jitcsde, y
+	units, B, T = 48, 11, 0.4
+	A = np.random.default_rng(7).random((units, units))
+	fs = [y(i) - y(i) ** 3 / 3 - y(units + i) + 0.5 + sum(float(A[i, j]) / units * (y(j) - y(i)) for j in range(units)) for i in range(units)]
+	fs += [0.08 * (y(i) + 0.7 - 0.8 * y(units + i)) for i in range(units)]
+	gs = [sympy.Float(0.05)] * units + [sympy.Float(0.0)] * units
+	SDE = jitcsde(fs, gs, ensemble=B, verbose=False)
+	assert SDE.spec.wide and SDE.spec.coupling_units == units
+	y0 = sharding.global_initial_states(0, B, 2 * units)
+	SDE.set_seed(sharding.global_seeds(0, B))
+	SDE.set_initial_value(y0, 0.0)
+	out = SDE.integrate(T)
+	ref = port.run_ensemble(SDE.spec, y0, sharding.global_seeds(0, B), 0.0, T)
+	assert_bits_equal(out, ref["y"], "symbolic wide model vs oracle")
+
+
+# ---- opt-in FP64 tensor-core coupling ("coupling = dmma"): the tolerance tier ---------------------------------------------
+def run_with_coupling(spec, B, T, coupling, y0=None):
+	y0 = sharding.global_initial_states(0, B, spec.n) if y0 is None else y0
+	E = Ensemble(spec, B)
+	E.set_option("coupling", coupling)
+	E.seed(sharding.global_seeds(0, B))
+	E.set_state(y0, 0.0)
+	E.set_integration_parameters(ControllerParameters())
+	stats = E.integrate(T)
+	_, acc, rej = E.controller_state()
+	return E.get_state(), acc.astype(np.int64), rej.astype(np.int64), stats
+
+
+@pytest.mark.parametrize("name,B,tpb", [("fhn_small", 23, 7), ("fhn_small", 10, 4), ("fhn_small_mult", 9, 7)])
+def test_dmma_coupling_within_the_tolerance_tier(monkeypatch, name, B, tpb):
+	"""mma.sync m8n8k4 fuses and re-associates the coupling sums: not bit-exact by construction.  BASELINE.json's tolerance
+	tier applies: a few steps agree to 1e-12, whole trajectories to 1e-9 wherever the accepted-step sequence is the same."""
+	monkeypatch.setenv("JSDE_WIDE_TPB", str(tpb))
+	spec = models.ALL[name]
+	ye, ae, re_, _ = run_with_coupling(spec, B, 0.02, "exact")
+	yd, ad, rd, _ = run_with_coupling(spec, B, 0.02, "dmma")
+	assert (ae == ad).all() and (re_ == rd).all()
+	np.testing.assert_allclose(yd, ye, rtol=1e-12, atol=1e-14)
+	assert not np.array_equal(yd, ye), "the tensor-core path was not taken"
+	ye, ae, re_, _ = run_with_coupling(spec, B, 1.0, "exact")
+	yd, ad, rd, _ = run_with_coupling(spec, B, 1.0, "dmma")
+	same = (ae == ad) & (re_ == rd)
+	assert same.mean() >= 0.8
+	np.testing.assert_allclose(yd[same], ye[same], rtol=1e-9, atol=1e-12)
+	# and against the oracle itself, same tier
+	ref = port.run_ensemble(spec, sharding.global_initial_states(0, B, spec.n), sharding.global_seeds(0, B), 0.0, 1.0)
+	same = (ref["accepted"] == ad) & (ref["rejected"] == rd)
+	np.testing.assert_allclose(yd[same], ref["y"][same], rtol=1e-9, atol=1e-12)
+
+
+def test_dmma_needs_a_free_column_and_a_coupling_term(monkeypatch):
+	monkeypatch.setenv("JSDE_WIDE_TPB", "8")  # eight live trajectories leave no column for the row sums: exact path
+	ye, *_ = run_with_coupling(models.fhn_small, 16, 0.3, "exact")
+	yd, *_ = run_with_coupling(models.fhn_small, 16, 0.3, "dmma")
+	assert_bits_equal(yd, ye, "8 trajectories per block fall back to the exact path")
+	E = Ensemble(models.lorenz_additive, 4)
+	with pytest.raises(JsdeError, match="wide models"):
+		E.set_option("coupling", "dmma")
+	with pytest.raises(JsdeError, match="unknown option"):
+		E.set_option("colour", "blue")
+
+
+def test_dmma_n1000_moments_within_three_standard_errors():
+	"""config 5's network: ensemble mean and variance of the tensor-core path against the exact path (other seeds would
+	add sampling noise only: the same seeds make this the sharper check) and per-trajectory agreement"""
+	spec, B, T = models.fhn_1000(), 64, 0.3
+	ye, ae, re_, se = run_with_coupling(spec, B, T, "exact")
+	yd, ad, rd, sd = run_with_coupling(spec, B, T, "dmma")
+	same = (ae == ad) & (re_ == rd)
+	assert same.mean() >= 0.8
+	np.testing.assert_allclose(yd[same], ye[same], rtol=1e-9, atol=1e-12)
+	se_mean = ye.std(axis=0, ddof=1) / np.sqrt(B)
+	assert (np.abs(yd.mean(axis=0) - ye.mean(axis=0)) <= 3 * se_mean + 1e-15).all()
+	var_e, var_d = ye.var(axis=0, ddof=1), yd.var(axis=0, ddof=1)
+	assert (np.abs(var_d - var_e) <= 3 * var_e * np.sqrt(2 / (B - 1)) + 1e-15).all()
