@@ -109,8 +109,9 @@ struct PairLayout {
 };
 
 // ---- consumer side: what Lane<> needs from its pair source ---------------------------------------------------------
-template <int N>
+template <int N, bool TAIL_ = false>
 struct PairConsumer {
+	static constexpr bool TAIL = TAIL_;  // see WarpRng
 	using L = PairLayout<N>;
 	double *base;
 	const double *log_tab;  // block-shared copy of glibc's log table {invc, logc}[128], followed by the pow tables
@@ -158,19 +159,20 @@ struct PairConsumer {
 };
 
 // ---- producer side ------------------------------------------------------------------------------------------------------
-template <int N>
+template <int N, bool TAIL = false>
 struct PairProducer {
 	using L = PairLayout<N>;
 	static constexpr int CAP = L::CAP;
 	double *base;
+	const double *log_tab;  // block-shared copy of glibc's log table (TAIL)
 	uint4 *mt;  // generator records [B][156]
 	int pair, lane;
 	int traj;            // this lane's trajectory (-1: none yet)
 	int wr, lvl, chunk;  // its ring write slot, (lower bound of the) fill level, next chunk
 	unsigned pushed;
 
-	__device__ __forceinline__ PairProducer(double *pair_smem, int pair_index, uint4 *records)
-		: base(pair_smem), mt(records), pair(pair_index), lane(threadIdx.x & 31), traj(-1), wr(0), lvl(0), chunk(0), pushed(0) {}
+	__device__ __forceinline__ PairProducer(double *pair_smem, const double *shared_log_tab, int pair_index, uint4 *records)
+		: base(pair_smem), log_tab(shared_log_tab), mt(records), pair(pair_index), lane(threadIdx.x & 31), traj(-1), wr(0), lvl(0), chunk(0), pushed(0) {}
 
 	__device__ __forceinline__ double *fx1_() const { return base; }
 	__device__ __forceinline__ double *fx2_() const { return base + CAP * RNG_STRIDE; }
@@ -279,6 +281,8 @@ struct PairProducer {
 				v.z = mt_temper(a.z);
 				v.w = mt_temper(a.w);
 				ok = polar_candidate(v, x1, x2, r2);
+				if (TAIL && ok)
+					r2 = polar_radius_factor_with(r2, log_tab);
 			}
 			const unsigned okm = __ballot_sync(full, ok);
 			const unsigned grp = (okm >> (g * RNG_GROUP)) & 0xffu;

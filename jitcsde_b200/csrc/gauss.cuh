@@ -48,4 +48,11 @@ __device__ __forceinline__ double polar_radius_factor(double r2)
 	return sqrt(__ddiv_rn(__dmul_rn(-2.0, jsde_log(r2)), r2));
 }
 
+// the same with glibc's log table in shared memory (`log_tab`, may be null: global table)
+__device__ __forceinline__ double polar_radius_factor_with(double r2, const double *log_tab)
+{
+	const double lg = jsde_log_is_near_one(r2) ? jsde_log_near_one(r2) : jsde_log_table_from(r2, log_tab);
+	return sqrt(__ddiv_rn(__dmul_rn(-2.0, lg), r2));
+}
+
 }  // namespace jsde

@@ -1,6 +1,6 @@
 // extern "C" boundary (include/jsde.h) for WIDE models (one thread block per group of trajectories, wide.cuh).  Same ABI
-// as jsde_abi.cu (shared plumbing: abi_common.cuh); the entry points the wide path does not implement (single-step
-// surface, pin_noise, the generator debug stream) return JSDE_E_STATE with a message instead of pretending.
+// as jsde_abi.cu (shared plumbing: abi_common.cuh), including the single-step surface and pin_noise; what the wide path
+// does not implement (per-trajectory control parameters, the generator debug stream) returns JSDE_E_STATE with a message.
 // Must be compiled with -fmad=false.
 #include "glibc_math.h"
 #include "wide.cuh"
@@ -22,6 +22,7 @@ static_assert(Model::WIDE, "jsde_abi_wide.cu is for wide models");
 struct jsde_handle : HandleBase {
 	int tpb = 1;  // trajectories per thread block (wide.cuh)
 	WideView v{};
+	double *staging = nullptr;  // [B][n]: host-supplied per-trajectory vectors (step sizes, jump amplitudes, masks)
 };
 
 namespace {
@@ -41,6 +42,10 @@ int reset_integrator(jsde_handle *h)
 	CU(cudaMemsetAsync(h->v.rejected, 0, B * sizeof(unsigned long long), h->stream));
 	CU(cudaMemsetAsync(h->v.jump_set, 0, B, h->stream));
 	CU(cudaMemsetAsync(h->v.tape_pos, 0, B * sizeof(long long), h->stream));
+	CU(cudaMemsetAsync(h->v.cursor, 0, B * sizeof(int), h->stream));
+	CU(cudaMemsetAsync(h->v.h_last, 0, B * sizeof(double), h->stream));
+	CU(cudaMemsetAsync(h->v.sNY, 0, (size_t)B * Model::N * sizeof(double), h->stream));
+	CU(cudaMemsetAsync(h->v.sErr, 0, (size_t)B * Model::N * sizeof(double), h->stream));
 	k_iota_rows<<<grid_for(B * h->D, 256), 256, 0, h->stream>>>(h->v.order, B, h->D);
 	CU(cudaGetLastError());
 	h->seed_dirty = true;
@@ -60,43 +65,49 @@ int ensure_seeded(jsde_handle *h)
 // One block integrates `tpb` trajectories (wide.cuh).  tpb is chosen so that the ensemble fills the GPU's block slots
 // (2 blocks per SM) in one wave where possible: 2^11 trajectories on 148 SMs -> 7 per block, 293 blocks on 296 slots.
 template <int T>
-int launch_one(jsde_handle *h, double target_time, const double *grid_times, int grid_count, double *grid_out)
+int launch_one(jsde_handle *h, double target_time, const double *grid_times, int grid_count, double *grid_out, const WideMode &wm)
 {
 	const size_t smem = wide_smem_bytes<Model, T>();
 	CU(cudaFuncSetAttribute(k_wide_integrate<Model, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_wide_integrate<Model, T><<<grid_for(h->B, T), WBLOCK, smem, h->stream>>>(h->v, h->ctrl, target_time, grid_times, grid_count, grid_out);
+	k_wide_integrate<Model, T><<<grid_for(h->B, T), WBLOCK, smem, h->stream>>>(h->v, h->ctrl, target_time, grid_times, grid_count, grid_out, wm);
 	CU(cudaGetLastError());
 	return JSDE_OK;
 }
 
-int launch_integrate(jsde_handle *h, double target_time, const double *grid_times = nullptr, int grid_count = 0, double *grid_out = nullptr)
+int launch_integrate(jsde_handle *h, double target_time, const double *grid_times = nullptr, int grid_count = 0, double *grid_out = nullptr,
+	const WideMode &wm = WideMode{WIDE_INTEGRATE, nullptr, 0u, 0.0})
 {
 	switch (h->tpb) {
-	case 1: return launch_one<1>(h, target_time, grid_times, grid_count, grid_out);
-	case 2: return launch_one<2>(h, target_time, grid_times, grid_count, grid_out);
-	case 4: return launch_one<4>(h, target_time, grid_times, grid_count, grid_out);
-	case 6: return launch_one<6>(h, target_time, grid_times, grid_count, grid_out);
-	case 7: return launch_one<7>(h, target_time, grid_times, grid_count, grid_out);
-	default: return launch_one<8>(h, target_time, grid_times, grid_count, grid_out);
+	case 1: return launch_one<1>(h, target_time, grid_times, grid_count, grid_out, wm);
+	case 2: return launch_one<2>(h, target_time, grid_times, grid_count, grid_out, wm);
+	case 4: return launch_one<4>(h, target_time, grid_times, grid_count, grid_out, wm);
+	case 7: return launch_one<7>(h, target_time, grid_times, grid_count, grid_out, wm);
+	case 8: return launch_one<8>(h, target_time, grid_times, grid_count, grid_out, wm);
+	default:
+		if constexpr (TMAX >= 16) {
+			if (h->tpb == 14) return launch_one<14>(h, target_time, grid_times, grid_count, grid_out, wm);
+			return launch_one<16>(h, target_time, grid_times, grid_count, grid_out, wm);
+		}
+		return launch_one<8>(h, target_time, grid_times, grid_count, grid_out, wm);
 	}
 }
 
 int choose_tpb(int device, int64_t B)
 {
-	static const int allowed[] = {1, 2, 4, 6, 7, 8};
+	static const int allowed[] = {1, 2, 4, 7, 8, 14, 16};
 	if (const char *env = getenv("JSDE_WIDE_TPB")) {  // development / test knob
 		const int want = atoi(env);
 		for (int a : allowed)
-			if (a == want) return a;
+			if (a == want && a <= TMAX) return a;
 	}
 	cudaDeviceProp prop;
 	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
 		return 8;
-	const int64_t slots = 2 * (int64_t)prop.multiProcessorCount;
+	const int64_t slots = WBLOCKS_PER_SM * (int64_t)prop.multiProcessorCount;
 	const int64_t need = (B + slots - 1) / slots;  // trajectories per block for a single wave
 	for (int a : allowed)
-		if (a >= need) return a;
-	return 8;
+		if (a >= need && a <= TMAX) return a;
+	return TMAX;
 }
 
 }  // namespace
@@ -140,6 +151,7 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	ALLOC(v.key, B * MT_WORDS); ALLOC(v.pos, B);
 	ALLOC(v.arg, B * n); ALLOC(v.sW, B * n); ALLOC(v.sZ, B * n); ALLOC(v.sF1, B * n); ALLOC(v.sNY, B * n);
 	ALLOC(v.next_jump, B); ALLOC(v.jump_set, B); ALLOC(v.tape_pos, B);
+	ALLOC(v.sErr, B * n); ALLOC(v.h_last, B); ALLOC(v.cursor, B); ALLOC(h->staging, B * n);
 	if (!Model::ADDITIVE) {
 		ALLOC(v.argA, B * n); ALLOC(v.argB, B * n); ALLOC(v.argC, B * n); ALLOC(v.sG2, B * n); ALLOC(v.sG3, B * n);
 	}
@@ -406,14 +418,128 @@ int jsde_set_time(jsde_t *h, const double *t_host)
 	return JSDE_OK;
 }
 
-int jsde_pin_noise(jsde_t *, unsigned, double) { return unsupported("pin_noise"); }
-int jsde_pin_noise_path(jsde_t *, unsigned, const double *, const double *, const double *) { return unsupported("pin_noise_path"); }
-int jsde_get_next_step(jsde_t *, const double *) { return unsupported("the single-step surface"); }
-int jsde_get_p(jsde_t *, double, double, double *) { return unsupported("the single-step surface"); }
-int jsde_accept_step(jsde_t *, const uint8_t *) { return unsupported("the single-step surface"); }
-int jsde_apply_jump(jsde_t *, const double *) { return unsupported("apply_jump"); }
+// ---- single-step surface (reference core methods, jitced_template.c:252-267, 396-545), one launch each ----------------------
+int jsde_pin_noise(jsde_t *h, unsigned number, double step)
+{
+	if (!h || !(step > 0.0))
+		return fail(JSDE_E_ARG, "Wrong input.");
+	if (number == 0)
+		return JSDE_OK;
+	int rc = bind(h);
+	if (rc) return rc;
+	if ((rc = ensure_seeded(h))) return rc;
+	h->v.use_jumps = 0;
+	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
+	if ((rc = launch_integrate(h, 0.0, nullptr, 0, nullptr, WideMode{WIDE_PIN, nullptr, number, step}))) return rc;
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_pin_noise_path(jsde_t *h, unsigned number, const double *steps_host, const double *dw_host, const double *dz_host)
+{
+	if (!h || (number && (!steps_host || !dw_host || !dz_host)))
+		return fail(JSDE_E_ARG, "Wrong input.");
+	for (unsigned j = 0; j < number; j++)
+		if (!(steps_host[j] > 0.0))
+			return fail(JSDE_E_ARG, "Wrong input. (step sizes must be positive)");
+	if (number == 0)
+		return JSDE_OK;
+	int rc = bind(h);
+	if (rc) return rc;
+	const size_t values = (size_t)h->B * number * Model::N;
+	Scratch scratch;
+	double *steps = nullptr, *dw = nullptr, *dz = nullptr;
+	if (scratch.get(&steps, number) != cudaSuccess || scratch.get(&dw, values) != cudaSuccess || scratch.get(&dz, values) != cudaSuccess)
+		return fail(JSDE_E_NOMEM, "pin_noise_path: the increments do not fit in device memory");
+	CU(cudaMemcpyAsync(steps, steps_host, number * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(dw, dw_host, values * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(dz, dz_host, values * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	k_wide_pin_path<Model::N><<<(unsigned)h->B, 256, 0, h->stream>>>(h->v, number, steps, dw, dz);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_get_next_step(jsde_t *h, const double *h_host)
+{
+	if (!h || !h_host)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc = bind(h);
+	if (rc) return rc;
+	if ((rc = ensure_seeded(h))) return rc;
+	h->v.use_jumps = 0;
+	CU(cudaMemcpyAsync(h->staging, h_host, h->B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemsetAsync(h->v.totals, 0, sizeof(CallTotals), h->stream));
+	if ((rc = launch_integrate(h, 0.0, nullptr, 0, nullptr, WideMode{WIDE_PROPOSE, h->staging, 0u, 0.0}))) return rc;
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_get_p(jsde_t *h, double atol, double rtol, double *p_host)
+{
+	if (!h || !p_host)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc = bind(h);
+	if (rc) return rc;
+	k_wide_get_p<Model::N><<<(unsigned)h->B, 256, 0, h->stream>>>(h->v, atol, rtol, h->staging);
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(p_host, h->staging, h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_accept_step(jsde_t *h, const uint8_t *mask_host)
+{
+	if (!h)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc = bind(h);
+	if (rc) return rc;
+	unsigned char *mask = nullptr;
+	if (mask_host) {
+		mask = reinterpret_cast<unsigned char *>(h->staging);
+		CU(cudaMemcpyAsync(mask, mask_host, h->B, cudaMemcpyHostToDevice, h->stream));
+	}
+	k_wide_accept<Model::N><<<(unsigned)h->B, 256, 0, h->stream>>>(h->v, mask);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_apply_jump(jsde_t *h, const double *change_host)
+{
+	if (!h || !change_host)
+		return fail(JSDE_E_ARG, "Wrong input. Note that the jump amplitudes must be an array of B*n doubles.");
+	int rc = bind(h);
+	if (rc) return rc;
+	const int64_t count = h->B * Model::N;
+	CU(cudaMemcpyAsync(h->staging, change_host, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	k_wide_add<<<grid_for(count, 256), 256, 0, h->stream>>>(h->v.y, h->staging, count);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(h->stream));
+	return JSDE_OK;
+}
+
+int jsde_dump_noise(jsde_t *h, int64_t b, double *out_host, int max_items, int *count)
+{
+	if (!h || b < 0 || b >= h->B || !out_host || !count || max_items < 0)
+		return fail(JSDE_E_ARG, "Wrong input.");
+	int rc = bind(h);
+	if (rc) return rc;
+	constexpr int n = Model::N;
+	CU(cudaStreamSynchronize(h->stream));
+	CU(cudaMemcpy(count, h->v.q_count + b, sizeof(int), cudaMemcpyDeviceToHost));
+	std::vector<int> order(h->D);
+	CU(cudaMemcpy(order.data(), h->v.order + b * h->D, h->D * sizeof(int), cudaMemcpyDeviceToHost));
+	const int width = 1 + 2 * n;
+	for (int d = 0; d < *count && d < max_items; d++) {
+		const int slot = order[d];
+		CU(cudaMemcpy(out_host + (size_t)d * width, h->v.qh + b * h->D + slot, sizeof(double), cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(out_host + (size_t)d * width + 1, h->v.qw + (b * h->D + slot) * 2 * n, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
+	}
+	return JSDE_OK;
+}
+
 int jsde_draw_gauss_debug(jsde_t *, double, int, double *) { return unsupported("the generator debug stream"); }
-int jsde_dump_noise(jsde_t *, int64_t, double *, int, int *) { return unsupported("dump_noise"); }
 // ---- checkpoint / restore: same contract as the lane library (include/jsde.h) ----------------------------------------
 namespace {
 struct WideCheckpointHeader {
@@ -433,6 +559,7 @@ Sections checkpoint_sections(jsde_handle *h)
 		{v.y, B * n * 8}, {v.t, B * 8}, {v.dt, B * 8}, {v.qh, B * D * 8}, {v.qw, B * D * 2 * n * 8}, {v.order, B * D * 4},
 		{v.q_count, B * 4}, {v.key, B * MT_WORDS * 4}, {v.pos, B * 4}, {v.status, B * 4}, {v.accepted, B * 8}, {v.rejected, B * 8},
 		{v.next_jump, B * 8}, {v.jump_set, B}, {v.tape_pos, B * 8},
+		{v.sNY, B * n * 8}, {v.sErr, B * n * 8}, {v.h_last, B * 8}, {v.cursor, B * 4},
 		{h->seeds, B * 4}, {h->par, (size_t)(Model::NPAR > 0 ? Model::NPAR : 1) * 8},
 	};
 }
@@ -453,7 +580,7 @@ int jsde_checkpoint_save(jsde_t *h, void *blob_host, int64_t bytes)
 	if (rc) return rc;
 	if ((rc = ensure_seeded(h))) return rc;
 	WideCheckpointHeader hd{};
-	hd.magic = WIDE_CHECKPOINT_MAGIC; hd.version = 1; hd.n = Model::N; hd.D = h->D; hd.npar = Model::NPAR; hd.B = h->B;
+	hd.magic = WIDE_CHECKPOINT_MAGIC; hd.version = 2; hd.n = Model::N; hd.D = h->D; hd.npar = Model::NPAR; hd.B = h->B;
 	hd.ctrl = h->ctrl; hd.first_step = h->first_step;
 	char *out = static_cast<char *>(blob_host);
 	memcpy(out, &hd, sizeof(hd));
@@ -467,7 +594,7 @@ int jsde_checkpoint_restore(jsde_t *h, const void *blob_host, int64_t bytes)
 	WideCheckpointHeader hd;
 	const char *in = static_cast<const char *>(blob_host);
 	memcpy(&hd, in, sizeof(hd));
-	if (hd.magic != WIDE_CHECKPOINT_MAGIC || hd.version != 1 || hd.n != Model::N || hd.B != h->B || hd.D != h->D || hd.npar != Model::NPAR)
+	if (hd.magic != WIDE_CHECKPOINT_MAGIC || hd.version != 2 || hd.n != Model::N || hd.B != h->B || hd.D != h->D || hd.npar != Model::NPAR)
 		return fail(JSDE_E_ARG, "Wrong input. (checkpoint belongs to a different model or ensemble shape)");
 	int rc = bind(h);
 	if (rc) return rc;

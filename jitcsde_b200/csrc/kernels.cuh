@@ -11,6 +11,19 @@ namespace jsde {
 
 constexpr int BLOCK = 128;  // single-step kernels: one trajectory per thread
 
+// Who computes the scale-independent Gaussian factor s = sqrt(-2 log(r2)/r2) (warp_rng.cuh: TAIL): the stepper (default) or
+// the generator side.  One choice per model library — queue contents must mean the same to every kernel.  Round 2 measured
+// the generator-side variant (the idea: for multiplicative-noise models the producer warps idle more than half of the time):
+// SRI-Lorenz -2.4 %, Duffing +2.2 %, additive Lorenz -17 % (profiles/r02_tail_in_producer_ab.log) — bit-identical results
+// either way (the parity suite passes in both settings), so it stays a build-time knob and is off.
+#ifndef JSDE_RNG_TAIL
+#define JSDE_RNG_TAIL(additive) false
+#endif
+template <class Model>
+constexpr bool rng_tail = JSDE_RNG_TAIL(Model::ADDITIVE);
+template <class Model>
+using ModelRng = WarpRng<Model::N, rng_tail<Model>>;
+
 // ---- shared memory of the single-step kernels: one set of generator FIFOs per warp (warp_rng.cuh) ---------------------
 constexpr int LOG_TAB_DOUBLES = 256;  // {invc, logc}[128], shared by the block
 
@@ -19,7 +32,7 @@ constexpr size_t rng_smem_bytes() { return ((size_t)(BLOCK / 32) * WarpRng<Model
 
 // Whole block must call (contains a __syncthreads).
 template <class Model>
-__device__ __forceinline__ WarpRng<Model::N> make_rng(const EnsembleView &e, int64_t k, bool live)
+__device__ __forceinline__ ModelRng<Model> make_rng(const EnsembleView &e, int64_t k, bool live)
 {
 	extern __shared__ __align__(16) double jsde_smem[];
 	for (int i = threadIdx.x; i < 128; i += BLOCK) {
@@ -28,7 +41,7 @@ __device__ __forceinline__ WarpRng<Model::N> make_rng(const EnsembleView &e, int
 	}
 	__syncthreads();
 	const int warp = threadIdx.x >> 5;
-	return WarpRng<Model::N>(jsde_smem + LOG_TAB_DOUBLES + warp * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP, jsde_smem, e.mt, k - (threadIdx.x & 31), live);
+	return ModelRng<Model>(jsde_smem + LOG_TAB_DOUBLES + warp * WarpRng<Model::N>::SMEM_DOUBLES_PER_WARP, jsde_smem, e.mt, k - (threadIdx.x & 31), live);
 }
 
 // ---- the hot path -------------------------------------------------------------------------------------------------
@@ -56,7 +69,7 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE
 
 	if (warp >= DUO_PAIRS) {  // ---- producer warpgroup ----
 		setmaxnreg_dec<DuoConfig<N, Model::ADDITIVE>::PRODUCER_REGS>();
-		PairProducer<N> P(pair_smem, pair, e.mt);
+		PairProducer<N, rng_tail<Model>> P(pair_smem, jsde_smem, pair, e.mt);
 		P.run(e.rng_spill, e.rng_level, e.mt_chunk, e.B);
 		return;
 	}
@@ -67,8 +80,8 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE
 	// Sampling-grid mode (grid_times != nullptr): the lane integrates to grid_times[0], records its state in
 	// grid_out[0][·][k], goes on to grid_times[1], … — exactly the sequence of integrate() calls of
 	// examples/noisy_lorenz.py:95-96 (truncated last step + Brownian bridge at every sample time), in one launch.
-	PairConsumer<N> rng(pair_smem, jsde_smem, pair);
-	Lane<Model, PairConsumer<N>> L(e, 0, rng);
+	PairConsumer<N, rng_tail<Model>> rng(pair_smem, jsde_smem, pair);
+	Lane<Model, PairConsumer<N, rng_tail<Model>>> L(e, 0, rng);
 	// This lane starts with the trajectory of its global index and (RECYCLE) takes the next one from the pool whenever
 	// its trajectory is done (duo.cuh).  Results do not depend on which lane integrates a trajectory.
 	int k = -1;  // B < 2^31 (jsde_create)
@@ -264,9 +277,9 @@ __global__ void __launch_bounds__(BLOCK) k_get_next_step(EnsembleView e, const d
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	const bool live = k < e.B;
 	const int64_t kk = live ? k : 0;
-	WarpRng<Model::N> rng = make_rng<Model>(e, k, live);
+	ModelRng<Model> rng = make_rng<Model>(e, k, live);
 	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
-	Lane<Model> L(e, kk, rng);
+	Lane<Model, ModelRng<Model>> L(e, kk, rng);
 	bool go = false;
 	if (live) {
 		L.load();
@@ -287,8 +300,8 @@ __global__ void __launch_bounds__(BLOCK) k_get_p(EnsembleView e, double atol, do
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B)
 		return;
-	WarpRng<Model::N> rng(nullptr, nullptr, e.mt, 0, false);
-	Lane<Model> L(e, k, rng);
+	ModelRng<Model> rng(nullptr, nullptr, e.mt, 0, false);
+	Lane<Model, ModelRng<Model>> L(e, k, rng);
 	L.load_proposal();
 	p[k] = L.error_ratio(atol, rtol);
 }
@@ -299,8 +312,8 @@ __global__ void __launch_bounds__(BLOCK) k_accept_step(EnsembleView e, const uns
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B || (mask && !mask[k]))
 		return;
-	WarpRng<Model::N> rng(nullptr, nullptr, e.mt, 0, false);
-	Lane<Model> L(e, k, rng);
+	ModelRng<Model> rng(nullptr, nullptr, e.mt, 0, false);
+	Lane<Model, ModelRng<Model>> L(e, k, rng);
 	L.load();
 	L.load_proposal();
 	L.commit();
@@ -313,9 +326,9 @@ __global__ void __launch_bounds__(BLOCK) k_pin_noise(EnsembleView e, unsigned nu
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	const bool live = k < e.B;
 	const int64_t kk = live ? k : 0;
-	WarpRng<Model::N> rng = make_rng<Model>(e, k, live);
+	ModelRng<Model> rng = make_rng<Model>(e, k, live);
 	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
-	Lane<Model> L(e, kk, rng);
+	Lane<Model, ModelRng<Model>> L(e, kk, rng);
 	if (live)
 		L.load();
 	for (unsigned j = 0; j < number; j++) {
@@ -338,8 +351,8 @@ __global__ void __launch_bounds__(BLOCK) k_pin_path(EnsembleView e, unsigned num
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	if (k >= e.B)
 		return;
-	WarpRng<N> rng(nullptr, nullptr, e.mt, 0, false);
-	Lane<Model> L(e, k, rng);
+	ModelRng<Model> rng(nullptr, nullptr, e.mt, 0, false);
+	Lane<Model, ModelRng<Model>> L(e, k, rng);
 	L.load();
 	for (unsigned j = 0; j < number && L.status == TRAJ_OK; j++) {
 		double W[N], Z[N];
@@ -360,15 +373,20 @@ __global__ void __launch_bounds__(BLOCK) k_draw_gauss(EnsembleView e, double sca
 	const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
 	const bool live = k < e.B;
 	const int64_t kk = live ? k : 0;
-	WarpRng<Model::N> rng = make_rng<Model>(e, k, live);
+	ModelRng<Model> rng = make_rng<Model>(e, k, live);
 	rng.load(e.rng_spill, e.rng_level, e.mt_chunk, e.B, kk);
 	for (int j = 0; j < pairs; j++) {
 		rng.ensure(live, 1);
 		if (live) {
 			double x1, x2, r2;
 			rng.pop(x1, x2, r2);
-			const double lg = jsde_log_is_near_one(r2) ? jsde_log_near_one(r2) : jsde_log_table_from(r2, rng.log_tab);
-			const double f = scale * sqrt(__ddiv_rn(__dmul_rn(-2.0, lg), r2));
+			double f;
+			if constexpr (rng_tail<Model>)
+				f = scale * r2;  // the queue holds the factor itself
+			else {
+				const double lg = jsde_log_is_near_one(r2) ? jsde_log_near_one(r2) : jsde_log_table_from(r2, rng.log_tab);
+				f = scale * sqrt(__ddiv_rn(__dmul_rn(-2.0, lg), r2));
+			}
 			out[(k * pairs + j) * 2] = x1 * f;
 			out[(k * pairs + j) * 2 + 1] = x2 * f;
 		}

@@ -152,6 +152,17 @@ struct Lane {
 	// f = scale*sqrt(-2*log(r2)/r2), DW = x1*f, DZ = x2*f (random_numbers.c:127-129).
 	__device__ __forceinline__ void draw(double scale, double (&gW)[N], double (&gZ)[N])
 	{
+		if constexpr (Rng::TAIL) {  // the generator side has computed s = sqrt(-2*log(r2)/r2) already
+#pragma unroll
+			for (int i = 0; i < N; i++) {
+				double s;
+				rng.pop(gW[i], gZ[i], s);
+				const double f = scale * s;
+				gW[i] *= f;
+				gZ[i] *= f;
+			}
+			return;
+		}
 		double r2[N], lg[N];
 		unsigned pending = 0;  // components whose radius needs glibc's near-one log branch
 #pragma unroll

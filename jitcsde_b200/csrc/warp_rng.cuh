@@ -39,8 +39,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 
 constexpr int RNG_STAGE_CHUNKS = 18;   // staged words of one trajectory and slot (duo.cuh): chunks c..c+8 and c+99..c+107
 
-template <int N>
+// TAIL: the queue's third value is the scale-independent Gaussian factor s = sqrt(-2 log(r2)/r2) instead of r2 — the
+// generator side computes it, the stepper only multiplies by the scale (f = scale*s: the same bits as
+// random_numbers.c:127-129).  Chosen per model (kernels.cuh: rng_tail): for multiplicative-noise models the stepper is
+// the longer of the two roles in the fused kernel, and the producer warps have time to spare.
+template <int N, bool TAIL_ = false>
 struct WarpRng {
+	static constexpr bool TAIL = TAIL_;
 	// room for the pairs left over below two draws' need (2N-1) plus a full group: the producer warps of the fused
 	// integrate kernel (duo.cuh) keep every trajectory one draw ahead of its consumer; the spill format is shared
 	static constexpr int CAP = 2 * N - 1 + RNG_GROUP;
@@ -174,6 +179,8 @@ struct WarpRng {
 				v.z = mt_temper(w.a.z);
 				v.w = mt_temper(w.a.w);
 				ok = polar_candidate(v, x1, x2, r2);
+				if (TAIL && ok)
+					r2 = polar_radius_factor_with(r2, log_tab);
 			}
 			const unsigned okm = __ballot_sync(full, ok);
 			const unsigned grp = (okm >> (g * RNG_GROUP)) & 0xffu;

@@ -27,6 +27,7 @@
 #pragma once
 
 #include "ensemble.cuh"
+#include "exact_div.cuh"
 #include "gauss.cuh"
 #include "mt19937.cuh"
 #include "philox_jumps.h"
@@ -34,10 +35,21 @@
 namespace jsde {
 namespace wide {
 
-constexpr int WBLOCK = 256;
+// Block shape: 256 threads / up to 8 trajectories / two blocks per SM (default), or 512 threads / up to 16 trajectories /
+// one block per SM, where every A_ij fetched from L2 serves twice as many trajectories.  Round 2 measured the second shape
+// on the n = 1000 network (2^11 trajectories, t = 0..1): exact coupling 4.43e6 vs 4.77e6 attempts/s, tensor-core coupling
+// 5.53e6 vs 5.71e6 (profiles/r02_wide_block_shape_ab.log) — two independent blocks per SM overlap one block's
+// per-trajectory phases with the other's coupling phase, which is worth more than the halved L2 traffic.  Both shapes
+// pass the parity suite; the larger one stays a build option (-DJSDE_WIDE_BLOCK=512).
+#ifndef JSDE_WIDE_BLOCK
+#define JSDE_WIDE_BLOCK 256
+#endif
+constexpr int WBLOCK = JSDE_WIDE_BLOCK;
+static_assert(WBLOCK == 256 || WBLOCK == 512, "wide block shape");
 constexpr int WWARPS = WBLOCK / 32;
-constexpr int TMAX = 8;       // trajectories per block: one warp each in the per-trajectory phases
-constexpr int TPAD = 8;       // row stride of the coupling stage buffer [units][TPAD] (64-byte rows)
+constexpr int TMAX = WWARPS;  // trajectories per block: one warp each in the per-trajectory phases
+constexpr int TPAD = TMAX;    // row stride of the coupling stage buffer [units][TPAD]
+constexpr int WBLOCKS_PER_SM = WBLOCK == 256 ? 2 : 1;
 constexpr int CANDIDATES = MT_WORDS / 4;  // 156 per regenerated block
 constexpr int MAX_DEPTH = 64;
 
@@ -72,6 +84,20 @@ struct WideView {
 	long long jump_first;
 	// opt-in: the coupling sums as FP64 tensor-core products (coupling_phase_dmma) instead of the exact register tile
 	int dmma;
+	// single-step surface (the reference core's get_next_step / get_p / accept_step, jitced_template.c:396-536): the last
+	// proposal lives in sNY (new state), sErr (error estimate per component), h_last (its step) and cursor (noise items used)
+	double *sErr;    // [B][n]
+	double *h_last;  // [B]
+	int *cursor;     // [B]
+};
+
+// what one launch of k_wide_integrate does
+enum { WIDE_INTEGRATE = 0, WIDE_PROPOSE = 1, WIDE_PIN = 2 };
+struct WideMode {
+	int mode;
+	const double *h;      // WIDE_PROPOSE: step size per trajectory (get_next_step, jitced_template.c:396-406)
+	unsigned pin_number;  // WIDE_PIN: items to append (pin_noise, jitced_template.c:252-267)
+	double pin_step;
 };
 
 __global__ void k_wide_seed(uint32_t *key, int *pos, const uint32_t *seeds, int64_t B)
@@ -103,7 +129,7 @@ struct TrajShared {
 	double next_jump;
 	long long tape_pos;
 	int jump_set, to_jump, pending_jump, tape_exhausted;
-	unsigned jumps;
+	unsigned jumps, pins;
 };
 
 // The reference's batch twist (random_numbers.c:73-84) by ONE warp on a state in shared memory.  Within a phase,
@@ -206,67 +232,87 @@ __device__ __forceinline__ void coupling_phase_dmma(const double *__restrict__ A
 {
 	constexpr int ROW_TILES = (UNITS + 7) / 8;
 	constexpr int TPW = (ROW_TILES + WWARPS - 1) / WWARPS;  // row tiles per warp
-	constexpr int ONES = TPAD - 1;                           // the column that yields the row sums
+	constexpr int NT = TPAD / 8;                             // column tiles of the stage buffer
 	const int lane = tid & 31, warp = tid >> 5;
 	const int g = lane >> 2, q = lane & 3;  // fragment coordinates: A[g][q], B[q][g], D[g][2q], D[g][2q+1]
+	const int ones = active;                // the first free column yields the row sums (active < TPAD)
+	const int ntiles = ones / 8 + 1;        // column tiles that hold something
 	for (int j = tid; j < UNITS; j += WBLOCK)
-		SC[j * TPAD + ONES] = 1.0;
+		SC[j * TPAD + ones] = 1.0;
 	__syncthreads();
-	double acc[TPW][2];
+	double acc[TPW][NT][2];
 #pragma unroll
 	for (int m = 0; m < TPW; m++)
-		acc[m][0] = acc[m][1] = 0.0;
+#pragma unroll
+		for (int nt = 0; nt < NT; nt++)
+			acc[m][nt][0] = acc[m][nt][1] = 0.0;
 #pragma unroll 2
 	for (int k0 = 0; k0 < UNITS; k0 += 4) {
 		const int j = k0 + q;
 		const bool jin = j < UNITS;
-		const double b = jin ? SC[j * TPAD + g] : 0.0;
+		double b[NT];
+#pragma unroll
+		for (int nt = 0; nt < NT; nt++)
+			b[nt] = (jin && nt < ntiles) ? SC[j * TPAD + nt * 8 + g] : 0.0;
 		const double *Aj = AT + (size_t)(jin ? j : 0) * UNITS;
 #pragma unroll
 		for (int m = 0; m < TPW; m++) {
 			const int i = (warp + m * WWARPS) * 8 + g;
 			const double a = (jin && i < UNITS) ? __ldg(Aj + i) : 0.0;
-			dmma_m8n8k4(acc[m], a, b);
+#pragma unroll
+			for (int nt = 0; nt < NT; nt++)
+				if (nt < ntiles)
+					dmma_m8n8k4(acc[m][nt], a, b[nt]);
 		}
 	}
-	double yi[TPW][2];
+	double yi[TPW][NT][2];
 #pragma unroll
 	for (int m = 0; m < TPW; m++) {
 		const int i = (warp + m * WWARPS) * 8 + g;
-		yi[m][0] = i < UNITS ? SC[i * TPAD + 2 * q] : 0.0;
-		yi[m][1] = i < UNITS ? SC[i * TPAD + 2 * q + 1] : 0.0;
+#pragma unroll
+		for (int nt = 0; nt < NT; nt++) {
+			yi[m][nt][0] = i < UNITS ? SC[i * TPAD + nt * 8 + 2 * q] : 0.0;
+			yi[m][nt][1] = i < UNITS ? SC[i * TPAD + nt * 8 + 2 * q + 1] : 0.0;
+		}
 	}
 	__syncthreads();  // everybody has read the last y_j
+	const int ones_tile = ones >> 3, ones_lane = (lane & ~3) | ((ones & 7) >> 1), ones_odd = ones & 1;
 #pragma unroll
 	for (int m = 0; m < TPW; m++) {
 		const int i = (warp + m * WWARPS) * 8 + g;
-		const double rowsum = __shfl_sync(0xffffffffu, acc[m][1], (lane & ~3) | 3);  // D[g][7]
+		double r0 = acc[m][0][0], r1 = acc[m][0][1];
+#pragma unroll
+		for (int nt = 1; nt < NT; nt++)
+			if (nt == ones_tile) {
+				r0 = acc[m][nt][0];
+				r1 = acc[m][nt][1];
+			}
+		const double rowsum = __shfl_sync(0xffffffffu, ones_odd ? r1 : r0, ones_lane);  // D[g][ones]
 		if (i < UNITS) {
-			if (2 * q < active)
-				SC[i * TPAD + 2 * q] = acc[m][0] - yi[m][0] * rowsum;
-			if (2 * q + 1 < active)
-				SC[i * TPAD + 2 * q + 1] = acc[m][1] - yi[m][1] * rowsum;
-			if (q == 3)
-				SC[i * TPAD + ONES] = 0.0;  // columns of absent trajectories stay zero
+#pragma unroll
+			for (int nt = 0; nt < NT; nt++) {
+				const int col = nt * 8 + 2 * q;
+				if (col < active)
+					SC[i * TPAD + col] = acc[m][nt][0] - yi[m][nt][0] * rowsum;
+				if (col + 1 < active)
+					SC[i * TPAD + col + 1] = acc[m][nt][1] - yi[m][nt][1] * rowsum;
+			}
+			if (q == 0)
+				SC[i * TPAD + ones] = 0.0;  // columns of absent trajectories stay zero
 		}
 	}
 	__syncthreads();
 }
 
 // the block's live trajectories occupy the first `active` columns: run the variant unrolled for exactly that many
-template <int T, int UNITS>
+template <int T, int UNITS, int K = 1>
 __device__ __forceinline__ void coupling_dispatch(int active, const double *__restrict__ AT, double *SC, int tid)
 {
-	switch (active) {
-	case 1: coupling_phase<1, UNITS>(AT, SC, tid); break;
-	case 2: if (T >= 2) coupling_phase<(T >= 2 ? 2 : 1), UNITS>(AT, SC, tid); break;
-	case 3: if (T >= 3) coupling_phase<(T >= 3 ? 3 : 1), UNITS>(AT, SC, tid); break;
-	case 4: if (T >= 4) coupling_phase<(T >= 4 ? 4 : 1), UNITS>(AT, SC, tid); break;
-	case 5: if (T >= 5) coupling_phase<(T >= 5 ? 5 : 1), UNITS>(AT, SC, tid); break;
-	case 6: if (T >= 6) coupling_phase<(T >= 6 ? 6 : 1), UNITS>(AT, SC, tid); break;
-	case 7: if (T >= 7) coupling_phase<(T >= 7 ? 7 : 1), UNITS>(AT, SC, tid); break;
-	case 8: if (T >= 8) coupling_phase<(T >= 8 ? 8 : 1), UNITS>(AT, SC, tid); break;
-	default: break;
+	if constexpr (K <= T) {
+		if (active == K)
+			coupling_phase<K, UNITS>(AT, SC, tid);
+		else
+			coupling_dispatch<T, UNITS, K + 1>(active, AT, SC, tid);
 	}
 }
 
@@ -280,8 +326,8 @@ constexpr size_t wide_smem_bytes()
 // grid_out[0][b][·], goes on to grid_times[1], … — the sequence of integrate() calls of examples/noisy_lorenz.py:95-96
 // (truncated last step + Brownian bridge at every sample time) in one launch.
 template <class Model, int T>
-__global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Controller c, double target,
-	const double *__restrict__ grid_times, int grid_count, double *__restrict__ grid_out)
+__global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideView e, Controller c, double target,
+	const double *__restrict__ grid_times, int grid_count, double *__restrict__ grid_out, WideMode wm)
 {
 	static_assert(T >= 1 && T <= TMAX && T <= WWARPS, "one warp per trajectory");
 	constexpr int N = Model::N;
@@ -332,6 +378,7 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 					S.tape_pos = e.tape_pos[b];
 				}
 				S.acc = S.rej = S.fresh = 0;
+				S.pins = 0;
 				S.max_depth = 0;
 				S.cursor = 0;
 				S.accept = 0;
@@ -370,11 +417,15 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			// ---- what to integrate to (_jitcsde.py:614, :682-700; the sampling loop of examples/noisy_lorenz.py:95-96):
 			// apply a jump that is due, schedule the next one, record sample times that are already reached — until an
 			// attempt is due or the trajectory is done.  Every lane runs this on identical inputs; lane 0 publishes.
-			double cur_target = S.target, tgt = cur_target, next_jump = S.next_jump;
+			double tgt = 0.0;
+			bool still_running = true;
+			if (wm.mode == WIDE_INTEGRATE) {
+			double cur_target = S.target, next_jump = S.next_jump;
+			tgt = cur_target;
 			int gi = S.grid_index, jump_set = S.jump_set;
 			long long tape_pos = S.tape_pos;
 			unsigned jumped = 0;
-			bool to_jump = false, apply = S.pending_jump != 0, still_running = true, exhausted = false;
+			bool to_jump = false, apply = S.pending_jump != 0, exhausted = false;
 			double *const Ycur = e.y + b * N;
 			while (true) {
 				if (Model::HAS_JUMP && apply) {  // apply_jump(amp(time, state)) (:696-698) on the pre-jump state
@@ -444,11 +495,16 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 				if (!still_running)
 					S.running = 0;
 			}
+			}  // WIDE_INTEGRATE
 			__syncwarp();
 			if (still_running) {
 			double h;
 			bool last = false;
-			if (t + dt < tgt)
+			if (wm.mode == WIDE_PROPOSE)
+				h = wm.h[b];  // get_next_step(h): the caller's step, whatever the time is
+			else if (wm.mode == WIDE_PIN)
+				h = wm.pin_step;
+			else if (t + dt < tgt)
 				h = dt;
 			else {
 				h = tgt - t;
@@ -457,7 +513,7 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			int count = S.count, pos = S.pos;
 			bool started = false, overflow = false;
 			double need = h, hq = 0.0;
-			int cur = 0;
+			int cur = wm.mode == WIDE_PIN ? count : 0;  // pin_noise appends behind everything that is stored
 			while (need != 0.0 && cur < count) {
 				const int s = S.order[cur];
 				hq = S.qh[s];
@@ -487,7 +543,13 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 					const double scale = sqrt(variance);
 					const int snew = S.order[count];  // a free physical slot
 					const int s1 = bridging ? S.order[cur] : snew;
-					// n pairs in stream order (get_gauss, template:145-154): pair k belongs to component k
+					// n pairs in stream order (get_gauss, template:145-154): pair k belongs to component k.  Two passes, so that the
+					// sequential part (which candidate is the k-th accepted one) stays light and the heavy part (log, division,
+					// square root, bridge: ~100 dependent FP64 instructions per pair) runs four pairs per lane at a time:
+					// pass 1 parks the raw pairs (x1, x2) in the new item's own storage and r2 in the stage-argument scratch
+					// (free until P3), pass 2 turns them into increments.  Round 1 did both per 32-candidate strip and spent
+					// about a third of the n = 1000 kernel's time with seven warps waiting for the slowest draw.
+					double *const raw1 = qw + (snew * 2 + 0) * N, *const raw2 = qw + (snew * 2 + 1) * N, *const rawr = e.arg + b * N;
 					int produced = 0;
 					while (produced < N) {
 						if (pos == MT_WORDS) {
@@ -512,23 +574,9 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 						const int rank = __popc(okm & lt);
 						if (ok && rank < take) {
 							const int k = produced + rank;
-							const double f = scale * polar_radius_factor(r2);
-							double gw = x1 * f, gz = x2 * f;
-							if (bridging) {
-								const double w1 = qw[(s1 * 2 + 0) * N + k], z1 = qw[(s1 * 2 + 1) * N + k];
-								const double w2 = gw + w1 * factor, z2 = gz + z1 * factor;
-								gw = w1 - w2;
-								gz = z1 - z2;
-								qw[(snew * 2 + 0) * N + k] = w2;
-								qw[(snew * 2 + 1) * N + k] = z2;
-								qw[(s1 * 2 + 0) * N + k] = gw;
-								qw[(s1 * 2 + 1) * N + k] = gz;
-							} else {
-								qw[(snew * 2 + 0) * N + k] = gw;
-								qw[(snew * 2 + 1) * N + k] = gz;
-							}
-							sW[k] = started ? sW[k] + gw : gw;
-							sZ[k] = started ? sZ[k] + gz : gz;
+							raw1[k] = x1;
+							raw2[k] = x2;
+							rawr[k] = r2;
 						}
 						// candidates up to the last pair taken are consumed; rejected ones behind it would be rejected
 						// again by the next draw, so a fully used strip may be skipped as a whole
@@ -537,6 +585,69 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 						else
 							pos += 4 * ((int)__fns(okm, 0, take) + 1);
 						produced += take;
+					}
+					__syncwarp();
+					// pass 2: f = scale*sqrt(-2*log(r2)/r2), DW = x1*f, DZ = x2*f (random_numbers.c:127-129), bridge, sums
+					constexpr int GROUP = 4;
+					for (int k0 = lane; k0 < N; k0 += 32 * GROUP) {
+						double x1[GROUP], x2[GROUP], r2[GROUP], lg[GROUP], f[GROUP];
+						unsigned pending = 0;
+#pragma unroll
+						for (int u = 0; u < GROUP; u++) {
+							const int k = k0 + 32 * u;
+							const bool in = k < N;
+							x1[u] = in ? raw1[k] : 0.0;
+							x2[u] = in ? raw2[k] : 0.0;
+							r2[u] = in ? rawr[k] : 0.5;
+							lg[u] = jsde_log_table_from(r2[u], nullptr);
+							if (jsde_log_is_near_one(r2[u]))
+								pending |= 1u << u;
+						}
+						while (pending) {  // glibc's near-one branch: rare, once per pair that needs it
+							const int which = __ffs(pending) - 1;
+							pending &= pending - 1;
+							double x = r2[0];
+#pragma unroll
+							for (int u = 1; u < GROUP; u++)
+								if (u == which)
+									x = r2[u];
+							const double v = jsde_log_near_one(x);
+#pragma unroll
+							for (int u = 0; u < GROUP; u++)
+								if (u == which)
+									lg[u] = v;
+						}
+						bool tame = true;
+#pragma unroll
+						for (int u = 0; u < GROUP; u++)
+							f[u] = scale * inline_sqrt(inline_div(__dmul_rn(-2.0, lg[u]), r2[u], tame), tame);
+						if (!tame) {  // cold: operands near the ends of the exponent range
+#pragma unroll
+							for (int u = 0; u < GROUP; u++)
+								f[u] = scale * sqrt(__ddiv_rn(__dmul_rn(-2.0, lg[u]), r2[u]));
+						}
+#pragma unroll
+						for (int u = 0; u < GROUP; u++) {
+							const int k = k0 + 32 * u;
+							if (k < N) {
+								double gw = x1[u] * f[u], gz = x2[u] * f[u];
+								if (bridging) {
+									const double w1 = qw[(s1 * 2 + 0) * N + k], z1 = qw[(s1 * 2 + 1) * N + k];
+									const double w2 = gw + w1 * factor, z2 = gz + z1 * factor;
+									gw = w1 - w2;
+									gz = z1 - z2;
+									raw1[k] = w2;
+									raw2[k] = z2;
+									qw[(s1 * 2 + 0) * N + k] = gw;
+									qw[(s1 * 2 + 1) * N + k] = gz;
+								} else {
+									raw1[k] = gw;
+									raw2[k] = gz;
+								}
+								sW[k] = started ? sW[k] + gw : gw;
+								sZ[k] = started ? sZ[k] + gz : gz;
+							}
+						}
 					}
 					__syncwarp();
 					if (lane == 0) {
@@ -574,6 +685,16 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			}
 		}
 		__syncthreads();
+		if (wm.mode == WIDE_PIN) {  // pin_noise (template:252-267): the appended item becomes the current one, nothing else happens
+			if (tid < T && ts[tid].running) {
+				TrajShared &S = ts[tid];
+				S.cursor = S.count - 1;
+				if (++S.pins >= wm.pin_number)
+					S.running = 0;
+			}
+			__syncthreads();
+			continue;
+		}
 
 		// Trajectories that attempt a step in this round, as a bit mask (uniform over the block).  Their coupled
 		// components occupy the FIRST popc(mask) columns of the stage buffer, so that a block whose trajectories have
@@ -705,6 +826,8 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 							const double E_D = (fh2 - fh1) / 6;
 							const double er = fabs(E_D) + fabs(E_N);
 							e.sNY[b * N + i] = ny;
+							if (wm.mode == WIDE_PROPOSE)
+								e.sErr[b * N + i] = er;  // get_p is a separate call there (template:502-526)
 							const double tol = c.atol + c.rtol * fabs(ny);  // get_p (template:502-526)
 							if (er != 0.0 || tol != 0.0) {
 								const double x = er / tol;
@@ -726,7 +849,10 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 		}
 
 		// ---- P6: controller (_jitcsde.py:581-595) and commit bookkeeping, one warp per trajectory ----------------------
-		if (warp < T && ts[warp].running) {
+		if (wm.mode == WIDE_PROPOSE) {  // get_next_step ends here: the proposal waits for get_p / accept_step
+			if (tid < T)
+				ts[tid].running = 0;
+		} else if (warp < T && ts[warp].running) {
 			TrajShared &S = ts[warp];
 			double p = 0.0;
 #pragma unroll
@@ -827,6 +953,9 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			e.dt[b] = S.dt;
 			e.pos[b] = S.pos;
 			e.q_count[b] = S.count;
+			e.cursor[b] = wm.mode == WIDE_INTEGRATE ? 0 : S.cursor;
+			if (wm.mode == WIDE_PROPOSE)
+				e.h_last[b] = S.h;
 			e.status[b] = S.status;
 			e.accepted[b] += S.acc;
 			e.rejected[b] += S.rej;
@@ -845,6 +974,103 @@ __global__ void __launch_bounds__(WBLOCK, 2) k_wide_integrate(WideView e, Contro
 			atomicMax(&e.totals->max_depth, S.max_depth);
 		}
 	}
+}
+
+// get_p (template:502-526) on the stored proposal: one block per trajectory
+template <int N>
+__global__ void __launch_bounds__(256) k_wide_get_p(WideView e, double atol, double rtol, double *p)
+{
+	__shared__ double part[8];
+	const int64_t b = blockIdx.x;
+	double worst = 0.0;
+	for (int i = threadIdx.x; i < N; i += 256) {
+		const double er = e.sErr[b * N + i];
+		const double tol = atol + rtol * fabs(e.sNY[b * N + i]);
+		if (er != 0.0 || tol != 0.0) {  // a 0/0 component is skipped; a NaN never wins the comparison
+			const double x = er / tol;
+			if (x > worst)
+				worst = x;
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		const double other = __shfl_xor_sync(0xffffffffu, worst, o);
+		worst = other > worst ? other : worst;
+	}
+	if ((threadIdx.x & 31) == 0)
+		part[threadIdx.x >> 5] = worst;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < 8; w++)
+			worst = part[w] > worst ? part[w] : worst;
+		p[b] = worst;
+	}
+}
+
+// accept_step (template:528-536): commit the proposal, drop the consumed noise items (their slots rotate behind the ones in use)
+template <int N>
+__global__ void __launch_bounds__(256) k_wide_accept(WideView e, const unsigned char *mask)
+{
+	const int64_t b = blockIdx.x;
+	if (mask && !mask[b])
+		return;
+	for (int i = threadIdx.x; i < N; i += 256)
+		e.y[b * N + i] = e.sNY[b * N + i];
+	if (threadIdx.x == 0) {
+		e.t[b] = e.t[b] + e.h_last[b];
+		const int cursor = e.cursor[b], count = e.q_count[b];
+		int *order = e.order + b * e.D;
+		if (cursor > 0) {
+			int freed[MAX_DEPTH];
+			for (int d = 0; d < cursor; d++)
+				freed[d] = order[d];
+			for (int d = cursor; d < count; d++)
+				order[d - cursor] = order[d];
+			for (int d = 0; d < cursor; d++)
+				order[count - cursor + d] = freed[d];
+		}
+		e.q_count[b] = count - cursor;
+		e.cursor[b] = 0;
+	}
+}
+
+// pin_noise with caller-supplied increments (jsde_pin_noise_path): item j has length steps[j], DW = dw[b][j][.], DZ = dz[b][j][.]
+template <int N>
+__global__ void __launch_bounds__(256) k_wide_pin_path(WideView e, unsigned number, const double *steps, const double *dw, const double *dz)
+{
+	const int64_t b = blockIdx.x;
+	if (e.status[b] != TRAJ_OK)
+		return;
+	__shared__ int slot_s, stop_s;
+	for (unsigned j = 0; j < number; j++) {
+		if (threadIdx.x == 0) {
+			const int count = e.q_count[b];
+			stop_s = count >= e.D;
+			if (stop_s)
+				e.status[b] = TRAJ_NOISE_OVERFLOW;
+			else {
+				slot_s = e.order[b * e.D + count];
+				e.qh[b * e.D + slot_s] = steps[j];
+				e.q_count[b] = count + 1;
+				e.cursor[b] = count;  // the newest item is the current one (template:173)
+			}
+		}
+		__syncthreads();
+		if (stop_s)
+			return;
+		double *item = e.qw + (b * e.D + slot_s) * 2 * N;
+		for (int i = threadIdx.x; i < N; i += 256) {
+			item[i] = dw[(b * number + j) * N + i];
+			item[N + i] = dz[(b * number + j) * N + i];
+		}
+		__syncthreads();
+	}
+}
+
+__global__ void k_wide_add(double *y, const double *change, int64_t count)
+{
+	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx < count)
+		y[idx] += change[idx];
 }
 
 __global__ void k_iota_rows(int *order, int64_t B, int D)

@@ -48,8 +48,28 @@ def test_single_step_with_cuda_libm_calls_within_1e13():
 
 
 def test_trajectories_with_cuda_libm_calls_within_1e9_where_the_step_sequence_matches():
-	"""rung 4: whole trajectories of a contracting system; compared only where the accepted/rejected counts agree"""
-	spec, B, T = models.pendulum, 256, 2.0
+	"""rung 4.  "Where the accepted-step sequence matches" means the same step SIZES: with the adaptive controller a
+	last-bit difference in sin/cos changes the error estimate, hence the next step size by a relative 1e-9 or so, hence every
+	later Wiener increment (DW = x*sqrt(h)) — the two sides then integrate different discretisations of the path.  A
+	controller that never rejects and never changes the step pins the sequence; 500 steps then agree to 1e-9."""
+	spec, B, T = models.pendulum, 256, 1.0
+	pinned = dict(first_step=2e-3, max_step=2e-3, atol=1e-2, rtol=1e-2)
+	y0, seeds = ensemble_inputs(spec.n, B)
+	E = Ensemble(spec, B)
+	E.seed(seeds)
+	E.set_state(y0, 0.0)
+	E.set_integration_parameters(ControllerParameters(**pinned))
+	E.integrate(T)
+	y = E.get_state()
+	_, acc, rej = E.controller_state()
+	ref = port.run_ensemble(spec, y0, seeds, 0.0, T, **pinned)
+	assert (acc.astype(np.int64) == ref["accepted"]).all() and (rej == 0).all() and (ref["rejected"] == 0).all()
+	np.testing.assert_allclose(y, ref["y"], rtol=1e-9, atol=1e-12)
+
+
+def test_adaptive_trajectories_with_cuda_libm_calls_agree_statistically():
+	"""rung 5 for the same model with the default controller: ensemble moments within 3 standard errors of the oracle's"""
+	spec, B, T = models.pendulum, 4096, 1.0
 	y0, seeds = ensemble_inputs(spec.n, B)
 	E = Ensemble(spec, B)
 	E.seed(seeds)
@@ -57,12 +77,11 @@ def test_trajectories_with_cuda_libm_calls_within_1e9_where_the_step_sequence_ma
 	E.set_integration_parameters(ControllerParameters())
 	E.integrate(T)
 	y = E.get_state()
-	_, acc, rej = E.controller_state()
-	ref = port.run_ensemble(spec, y0, seeds, 0.0, T)
-	same = (acc.astype(np.int64) == ref["accepted"]) & (rej.astype(np.int64) == ref["rejected"])
-	assert same.mean() > 0.9, f"only {same.sum()} of {B} trajectories kept the oracle's step sequence"
-	np.testing.assert_allclose(y[same], ref["y"][same], rtol=1e-9, atol=1e-12)
-	# the others took a different accept/reject decision somewhere: still the same SDE, statistically
+	Bo = 1024
+	ref = port.run_ensemble(spec, y0[:Bo], seeds[:Bo] + np.uint32(500_000), 0.0, T)["y"]
+	for i in range(2):
+		se = np.sqrt(y[:, i].var() / B + ref[:, i].var() / Bo)
+		assert abs(y[:, i].mean() - ref[:, i].mean()) <= 3 * se
 	assert np.isfinite(y).all() and (E.t == T).all()
 
 

@@ -21,7 +21,7 @@ def run(spec, B, T, **ctrl):
 	return E, E.integrate(T), y0
 
 
-@pytest.mark.parametrize("tpb", [1, 2, 4, 7, 8])
+@pytest.mark.parametrize("tpb", [1, 2, 4, 7, 8])  # (14 and 16 as well in a -DJSDE_WIDE_BLOCK=512 build: checked in round 2)
 def test_small_network_vs_oracle(monkeypatch, tpb):
 	monkeypatch.setenv("JSDE_WIDE_TPB", str(tpb))  # trajectories per thread block (37 = 4*8 + 5: a ragged last block)
 	spec = models.fhn_small  # n = 48, 24 coupled units
@@ -154,11 +154,98 @@ def test_wide_failure_paths_and_unsupported_calls():
 	E, stats, _ = run(spec, 4, 1.0, min_step=10.0, max_step=10.0, first_step=10.0)
 	assert stats["n_min_step"] == 4 and (E.status == 1).all()
 	with pytest.raises(JsdeError, match="not implemented for wide"):
-		E.pin_noise(1, 1e-3)
+		E.draw_gauss(1.0, 4)
 	with pytest.raises(JsdeError, match="without a jump amplitude"):
 		E.integrate_jumps(1.0, np.ones((4, 2)), np.ones((4, 2)))
-	with pytest.raises(JsdeError, match="not implemented for wide"):
-		E.get_next_step(1e-3)
+
+
+@pytest.mark.parametrize("name,tpb", [("fhn_small", 1), ("fhn_small", 7), ("fhn_small_mult", 4)])
+def test_wide_single_step_surface_vs_oracle(monkeypatch, name, tpb):
+	"""the reference core's own methods (jitced_template.c:252-267, 396-545) on the wide path, call by call against the
+	oracle: pin_noise, get_next_step (append, Brownian bridge, consume + append), get_p, accept_step (all / masked),
+	apply_jump, the writable time, the noise memory's contents"""
+	monkeypatch.setenv("JSDE_WIDE_TPB", str(tpb))
+	spec, B = models.ALL[name], 9
+	y0 = sharding.global_initial_states(0, B, spec.n)
+	seeds = sharding.global_seeds(0, B)
+	E = Ensemble(spec, B)
+	E.seed(seeds)
+	E.set_state(y0, 0.0)
+	cores = [port.PortCore(spec, y0[k], 0.0, int(seeds[k])) for k in range(B)]
+
+	def check(what):
+		assert_bits_equal(E.get_state(), np.array([c.get_state() for c in cores]), what + ": state")
+		assert_bits_equal(E.t, np.array([c.t for c in cores]), what + ": t")
+		for k in (0, B - 1):
+			assert_bits_equal(E.dump_noise(k), cores[k].dump_queue(), f"{what}: noise memory of trajectory {k}")
+
+	def step(h):
+		E.get_next_step(h)
+		for c in cores:
+			c.get_next_step(h)
+		assert_bits_equal(E.get_p(1e-10, 1e-5), np.array([c.get_p(1e-10, 1e-5) for c in cores]), f"p after get_next_step({h})")
+
+	def accept(mask=None):
+		E.accept_step(mask)
+		for k, c in enumerate(cores):
+			if mask is None or mask[k]:
+				c.accept_step()
+
+	E.pin_noise(3, 2e-4)
+	for c in cores:
+		c.pin_noise(3, 2e-4)
+	check("pin_noise")
+	step(1e-3)     # consumes the three pinned items, appends the rest
+	step(5e-4)     # rejected proposal replaced: consumes two and a half items -> Brownian bridge
+	step(1e-4)
+	accept()
+	check("accept after bridges")
+	step(3e-4)
+	accept(np.arange(B) % 2 == 0)  # masked: the odd trajectories keep their proposal unaccepted
+	check("masked accept")
+	step(2e-3)
+	accept()
+	E.pin_noise(2, 0.5)
+	for c in cores:
+		c.pin_noise(2, 0.5)
+	step(0.25)
+	step(1e-3)
+	accept()
+	check("second round")
+	change = np.random.default_rng(3).normal(size=(B, spec.n)) * 0.01
+	E.apply_jump(change)
+	for k, c in enumerate(cores):
+		c.apply_jump(change[k])
+	E.t = E.t + 0.125
+	for c in cores:
+		c.t = c.t + 0.125
+	step(1e-3)
+	accept()
+	check("after apply_jump and a time shift")
+	# the fused path continues from there
+	target = float(E.t.max()) + 0.05
+	E.set_integration_parameters(ControllerParameters())
+	E.integrate(target)
+	assert_bits_equal(E.get_state(), np.array([c.integrate(target) for c in cores]), "integrate after single steps")
+
+
+def test_wide_pin_noise_path_vs_oracle():
+	spec, B, K = models.fhn_small, 5, 4
+	y0 = sharding.global_initial_states(0, B, spec.n)
+	rng = np.random.default_rng(12)
+	steps = np.array([1e-3, 5e-4, 2e-3, 1e-3])
+	dw = rng.standard_normal((B, K, spec.n)) * np.sqrt(steps)[None, :, None]
+	dz = rng.standard_normal((B, K, spec.n)) * np.sqrt(steps)[None, :, None]
+	E = Ensemble(spec, B)
+	E.seed(sharding.global_seeds(0, B))
+	E.set_state(y0, 0.0)
+	E.set_integration_parameters(ControllerParameters())
+	E.pin_noise_path(steps, dw, dz)
+	E.integrate(0.01)
+	for k in range(B):
+		P = port.PortCore(spec, y0[k], 0.0, k)
+		P.pin_path(steps, dw[k], dz[k])
+		assert_bits_equal(E.get_state()[k], P.integrate(0.01), f"trajectory {k}")
 
 
 def test_wide_moments():
@@ -196,13 +283,20 @@ def test_symbolic_network_through_the_front_end():
 
 
 # ---- opt-in FP64 tensor-core coupling ("coupling = dmma"): the tolerance tier ---------------------------------------------
-def run_with_coupling(spec, B, T, coupling, y0=None):
-	y0 = sharding.global_initial_states(0, B, spec.n) if y0 is None else y0
+#: a controller that never rejects and never changes the step (loose tolerances, first_step = max_step): with adaptive
+#: steps a last-bit difference in the error estimate changes the next step size by a relative 1e-9 or so, and with it every
+#: later Wiener increment (DW = x*sqrt(h)) — "the accepted-step sequence matches" (BASELINE.json) means the same step
+#: SIZES, which only a pinned step guarantees across two arithmetic paths
+PINNED = dict(first_step=2e-3, max_step=2e-3, atol=1e-2, rtol=1e-2)
+
+
+def run_with_coupling(spec, B, T, coupling, **ctrl):
+	y0 = sharding.global_initial_states(0, B, spec.n)
 	E = Ensemble(spec, B)
 	E.set_option("coupling", coupling)
 	E.seed(sharding.global_seeds(0, B))
 	E.set_state(y0, 0.0)
-	E.set_integration_parameters(ControllerParameters())
+	E.set_integration_parameters(ControllerParameters(**ctrl))
 	stats = E.integrate(T)
 	_, acc, rej = E.controller_state()
 	return E.get_state(), acc.astype(np.int64), rej.astype(np.int64), stats
@@ -211,47 +305,50 @@ def run_with_coupling(spec, B, T, coupling, y0=None):
 @pytest.mark.parametrize("name,B,tpb", [("fhn_small", 23, 7), ("fhn_small", 10, 4), ("fhn_small_mult", 9, 7)])
 def test_dmma_coupling_within_the_tolerance_tier(monkeypatch, name, B, tpb):
 	"""mma.sync m8n8k4 fuses and re-associates the coupling sums: not bit-exact by construction.  BASELINE.json's tolerance
-	tier applies: a few steps agree to 1e-12, whole trajectories to 1e-9 wherever the accepted-step sequence is the same."""
+	tier applies: with the same step sequence, trajectories agree to 1e-9 relative (measured: ~1e-13) with the exact path
+	and with the oracle; with the adaptive controller, the ensembles agree statistically."""
 	monkeypatch.setenv("JSDE_WIDE_TPB", str(tpb))
-	spec = models.ALL[name]
-	ye, ae, re_, _ = run_with_coupling(spec, B, 0.02, "exact")
-	yd, ad, rd, _ = run_with_coupling(spec, B, 0.02, "dmma")
-	assert (ae == ad).all() and (re_ == rd).all()
-	np.testing.assert_allclose(yd, ye, rtol=1e-12, atol=1e-14)
+	spec, T = models.ALL[name], 0.5
+	ye, ae, re_, _ = run_with_coupling(spec, B, T, "exact", **PINNED)
+	yd, ad, rd, _ = run_with_coupling(spec, B, T, "dmma", **PINNED)
+	assert (ae == ad).all() and (re_ == rd).all() and (re_ == 0).all() and (ae == 250).all()
 	assert not np.array_equal(yd, ye), "the tensor-core path was not taken"
-	ye, ae, re_, _ = run_with_coupling(spec, B, 1.0, "exact")
-	yd, ad, rd, _ = run_with_coupling(spec, B, 1.0, "dmma")
-	same = (ae == ad) & (re_ == rd)
-	assert same.mean() >= 0.8
-	np.testing.assert_allclose(yd[same], ye[same], rtol=1e-9, atol=1e-12)
-	# and against the oracle itself, same tier
-	ref = port.run_ensemble(spec, sharding.global_initial_states(0, B, spec.n), sharding.global_seeds(0, B), 0.0, 1.0)
-	same = (ref["accepted"] == ad) & (ref["rejected"] == rd)
-	np.testing.assert_allclose(yd[same], ref["y"][same], rtol=1e-9, atol=1e-12)
+	np.testing.assert_allclose(yd, ye, rtol=1e-9, atol=1e-12)
+	ref = port.run_ensemble(spec, sharding.global_initial_states(0, B, spec.n), sharding.global_seeds(0, B), 0.0, T, **PINNED)
+	assert_bits_equal(ye, ref["y"], "exact path vs oracle, pinned steps")
+	np.testing.assert_allclose(yd, ref["y"], rtol=1e-9, atol=1e-12)
+	# default (adaptive) controller: the same SDE — ensemble means of the two paths within 3 standard errors of each other
+	ye, *_ = run_with_coupling(spec, B, T, "exact")
+	yd, *_ = run_with_coupling(spec, B, T, "dmma")
+	se = np.sqrt((ye.var(axis=0, ddof=1) + yd.var(axis=0, ddof=1)) / B)
+	assert (np.abs(yd.mean(axis=0) - ye.mean(axis=0)) <= 3 * se + 1e-12).all()
 
 
-def test_dmma_needs_a_free_column_and_a_coupling_term(monkeypatch):
-	monkeypatch.setenv("JSDE_WIDE_TPB", "8")  # eight live trajectories leave no column for the row sums: exact path
-	ye, *_ = run_with_coupling(models.fhn_small, 16, 0.3, "exact")
-	yd, *_ = run_with_coupling(models.fhn_small, 16, 0.3, "dmma")
-	assert_bits_equal(yd, ye, "8 trajectories per block fall back to the exact path")
+def test_dmma_option_is_checked():
 	E = Ensemble(models.lorenz_additive, 4)
 	with pytest.raises(JsdeError, match="wide models"):
 		E.set_option("coupling", "dmma")
 	with pytest.raises(JsdeError, match="unknown option"):
 		E.set_option("colour", "blue")
+	W = Ensemble(models.fhn_small, 4)
+	W.set_option("coupling", "dmma")
+	W.set_option("coupling", "exact")
+	with pytest.raises(JsdeError, match="unknown option"):
+		W.set_option("coupling", "fast")
 
 
-def test_dmma_n1000_moments_within_three_standard_errors():
-	"""config 5's network: ensemble mean and variance of the tensor-core path against the exact path (other seeds would
-	add sampling noise only: the same seeds make this the sharper check) and per-trajectory agreement"""
-	spec, B, T = models.fhn_1000(), 64, 0.3
-	ye, ae, re_, se = run_with_coupling(spec, B, T, "exact")
-	yd, ad, rd, sd = run_with_coupling(spec, B, T, "dmma")
-	same = (ae == ad) & (re_ == rd)
-	assert same.mean() >= 0.8
-	np.testing.assert_allclose(yd[same], ye[same], rtol=1e-9, atol=1e-12)
-	se_mean = ye.std(axis=0, ddof=1) / np.sqrt(B)
-	assert (np.abs(yd.mean(axis=0) - ye.mean(axis=0)) <= 3 * se_mean + 1e-15).all()
+def test_dmma_n1000_within_the_tolerance_tier():
+	"""config 5's network (n = 1000, 500 coupled units): pinned steps -> per-trajectory agreement; default controller ->
+	ensemble mean and variance of every component within 3 standard errors of the exact path's"""
+	spec, B, T = models.fhn_1000(), 64, 0.2
+	ye, ae, re_, _ = run_with_coupling(spec, B, T, "exact", **PINNED)
+	yd, ad, rd, _ = run_with_coupling(spec, B, T, "dmma", **PINNED)
+	assert (ae == ad).all() and (re_ == rd).all()
+	assert not np.array_equal(yd, ye)
+	np.testing.assert_allclose(yd, ye, rtol=1e-9, atol=1e-12)
+	ye, *_ = run_with_coupling(spec, B, T, "exact")
+	yd, *_ = run_with_coupling(spec, B, T, "dmma")
+	se_mean = np.sqrt((ye.var(axis=0, ddof=1) + yd.var(axis=0, ddof=1)) / B)
+	assert (np.abs(yd.mean(axis=0) - ye.mean(axis=0)) <= 3 * se_mean + 1e-12).all()
 	var_e, var_d = ye.var(axis=0, ddof=1), yd.var(axis=0, ddof=1)
-	assert (np.abs(var_d - var_e) <= 3 * var_e * np.sqrt(2 / (B - 1)) + 1e-15).all()
+	assert (np.abs(var_d - var_e) <= 3 * np.sqrt(2 / (B - 1)) * np.sqrt(var_e ** 2 + var_d ** 2) + 1e-12).all()
