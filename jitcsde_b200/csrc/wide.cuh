@@ -26,6 +26,8 @@
 // SRA1 for additive and SRIW1 for multiplicative noise (template:408-464); jumps from a tape or a counter-based generator.
 #pragma once
 
+#include <cstdio>
+
 #include "ensemble.cuh"
 #include "exact_div.cuh"
 #include "gauss.cuh"
@@ -115,8 +117,8 @@ __global__ void k_wide_seed(uint32_t *key, int *pos, const uint32_t *seeds, int6
 }
 
 // per-trajectory working set in shared memory
-struct TrajShared {
-	uint32_t key[MT_WORDS];
+struct alignas(16) TrajShared {
+	alignas(16) uint32_t key[MT_WORDS];
 	double qh[MAX_DEPTH];
 	int order[MAX_DEPTH];
 	double warp_max[WWARPS];
@@ -135,28 +137,35 @@ struct TrajShared {
 // The reference's batch twist (random_numbers.c:73-84) by ONE warp on a state in shared memory.  Within a phase,
 // word i needs the old words i and i+1 (and a word the phase does not touch), so every 32-word strip is read, the warp
 // synchronised, and only then written.
+// Words [LO, HI) of one phase: every lane reads the operands of its (up to eight) words, the warp synchronises, then the
+// words are written — eight independent loads per lane in flight instead of one strip of 32 words at a time (the strip
+// version spent ~3000 cycles per regeneration in shared-memory latency and warp barriers; eight regenerations per draw
+// of 1000 pairs were half of the per-trajectory phase).
+template <int LO, int HI, int TAP>
+__device__ __forceinline__ void twist_phase(uint32_t *key, int lane)
+{
+	constexpr int PER_LANE = (HI - LO + 31) / 32;
+	uint32_t v[PER_LANE];
+#pragma unroll
+	for (int u = 0; u < PER_LANE; u++) {
+		const int i = LO + lane + 32 * u;
+		v[u] = i < HI ? mt_twist(key[i], key[i + 1], key[i + TAP]) : 0u;
+	}
+	__syncwarp();
+#pragma unroll
+	for (int u = 0; u < PER_LANE; u++) {
+		const int i = LO + lane + 32 * u;
+		if (i < HI)
+			key[i] = v[u];
+	}
+	__syncwarp();
+}
+
 __device__ __forceinline__ void twist_warp(uint32_t *key, int lane)
 {
-	for (int i0 = 0; i0 < 227; i0 += 32) {  // kk < N-M: key[kk] = key[kk+M] ^ mix(key[kk], key[kk+1])
-		const int i = i0 + lane;
-		uint32_t v = 0;
-		if (i < 227)
-			v = mt_twist(key[i], key[i + 1], key[i + 397]);
-		__syncwarp();
-		if (i < 227)
-			key[i] = v;
-		__syncwarp();
-	}
-	for (int i0 = 227; i0 < 623; i0 += 32) {  // kk < N-1: key[kk] = key[kk+(M-N)] ^ mix(key[kk], key[kk+1])
-		const int i = i0 + lane;
-		uint32_t v = 0;
-		if (i < 623)
-			v = mt_twist(key[i], key[i + 1], key[i - 227]);
-		__syncwarp();
-		if (i < 623)
-			key[i] = v;
-		__syncwarp();
-	}
+	twist_phase<0, 227, 397>(key, lane);     // kk < N-M: key[kk] = key[kk+M] ^ mix(key[kk], key[kk+1]); taps are old words
+	twist_phase<227, 454, -227>(key, lane);  // kk < N-1: key[kk] = key[kk+(M-N)] ^ mix(key[kk], key[kk+1]); taps 0..226: new
+	twist_phase<454, 623, -227>(key, lane);  // ... taps 227..395: new, written by the phase before
 	if (lane == 0)
 		key[623] = mt_twist(key[623], key[0], key[396]);
 	__syncwarp();
@@ -342,6 +351,17 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 	const int live = (int)min((int64_t)T, e.B - b0);  // trajectories of this block
 	const int D = e.D;
 	const unsigned lt = (1u << lane) - 1u;
+#ifdef JSDE_WIDE_TIMING  // development aid: where a block's time goes, phase by phase (printed by block 0)
+	long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, ph_last = clock64(), sub_last = 0;
+	int ph_rounds = 0;
+#define JSDE_MARK(i) do { if (tid == 0) { const long long now_ = clock64(); ph[i] += now_ - ph_last; ph_last = now_; } } while (0)
+#define JSDE_SUBMARK_START() do { if (tid == 0) sub_last = clock64(); } while (0)
+#define JSDE_SUBMARK(i) do { if (tid == 0) { const long long now_ = clock64(); ph[i] += now_ - sub_last; sub_last = now_; } } while (0)
+#else
+#define JSDE_MARK(i) do { } while (0)
+#define JSDE_SUBMARK_START() do { } while (0)
+#define JSDE_SUBMARK(i) do { } while (0)
+#endif
 
 	// ---- load: warp w owns trajectory w --------------------------------------------------------------------------
 	if (warp < T) {
@@ -510,6 +530,7 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 				h = tgt - t;
 				last = true;
 			}
+			JSDE_SUBMARK_START();
 			int count = S.count, pos = S.pos;
 			bool started = false, overflow = false;
 			double need = h, hq = 0.0;
@@ -519,16 +540,38 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 				hq = S.qh[s];
 				if (!(hq <= need))
 					break;
-				for (int i = lane; i < N; i += 32) {
-					const double w = qw[(s * 2 + 0) * N + i], z = qw[(s * 2 + 1) * N + i];
-					sW[i] = started ? sW[i] + w : w;
-					sZ[i] = started ? sZ[i] + z : z;
+				// eight independent loads per array in flight, then the stores: written the plain way (load, add, store per
+				// component) every iteration waited for its own L2 round trip — the compiler may not move a load above a
+				// store that could alias it — and this loop alone took ~20 000 cycles per consumed item
+				constexpr int BATCH = 8;
+				const double *const itemW = qw + (s * 2 + 0) * N, *const itemZ = qw + (s * 2 + 1) * N;
+				for (int i0 = lane; i0 < N; i0 += 32 * BATCH) {
+					double w[BATCH], z[BATCH];
+#pragma unroll
+					for (int u = 0; u < BATCH; u++) {
+						const int i = i0 + 32 * u;
+						w[u] = i < N ? itemW[i] : 0.0;
+						z[u] = i < N ? itemZ[i] : 0.0;
+						if (started && i < N) {
+							w[u] = sW[i] + w[u];
+							z[u] = sZ[i] + z[u];
+						}
+					}
+#pragma unroll
+					for (int u = 0; u < BATCH; u++) {
+						const int i = i0 + 32 * u;
+						if (i < N) {
+							sW[i] = w[u];
+							sZ[i] = z[u];
+						}
+					}
 				}
 				started = true;
 				need -= hq;
 				cur++;
 			}
 			__syncwarp();  // the draw below hands component k to an arbitrary lane: make the partial sums visible
+			JSDE_SUBMARK(8);
 			if (need != 0.0) {
 				if (count >= D)
 					overflow = true;
@@ -551,42 +594,58 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 					// about a third of the n = 1000 kernel's time with seven warps waiting for the slowest draw.
 					double *const raw1 = qw + (snew * 2 + 0) * N, *const raw2 = qw + (snew * 2 + 1) * N, *const rawr = e.arg + b * N;
 					int produced = 0;
+					const uint4 *const chunks = reinterpret_cast<const uint4 *>(S.key);
 					while (produced < N) {
 						if (pos == MT_WORDS) {
 							twist_warp(S.key, lane);
 							pos = 0;
 						}
+						// two strips of 32 candidates per turn (two independent temper/polar chains per lane); the second one
+						// counts only if the first is used up entirely
 						const int c0 = pos >> 2;
-						const int cand = c0 + lane;
-						bool ok = false;
-						double x1 = 0.0, x2 = 0.0, r2 = 0.0;
-						if (cand < CANDIDATES) {
-							uint4 w;
-							w.x = mt_temper(S.key[4 * cand]);
-							w.y = mt_temper(S.key[4 * cand + 1]);
-							w.z = mt_temper(S.key[4 * cand + 2]);
-							w.w = mt_temper(S.key[4 * cand + 3]);
-							ok = polar_candidate(w, x1, x2, r2);
+						bool ok[2];
+						double x1[2], x2[2], r2[2];
+#pragma unroll
+						for (int u = 0; u < 2; u++) {
+							const int cand = c0 + 32 * u + lane;
+							ok[u] = false;
+							x1[u] = x2[u] = r2[u] = 0.0;
+							if (cand < CANDIDATES) {
+								const uint4 kw = chunks[cand];
+								uint4 w;
+								w.x = mt_temper(kw.x);
+								w.y = mt_temper(kw.y);
+								w.z = mt_temper(kw.z);
+								w.w = mt_temper(kw.w);
+								ok[u] = polar_candidate(w, x1[u], x2[u], r2[u]);
+							}
 						}
-						const unsigned okm = __ballot_sync(0xffffffffu, ok);
-						const int navail = __popc(okm);
-						const int take = min(navail, N - produced);
-						const int rank = __popc(okm & lt);
-						if (ok && rank < take) {
-							const int k = produced + rank;
-							raw1[k] = x1;
-							raw2[k] = x2;
-							rawr[k] = r2;
+#pragma unroll
+						for (int u = 0; u < 2; u++) {
+							const int cu = c0 + 32 * u;
+							if (u == 1 && (cu >= CANDIDATES || produced >= N || pos != 4 * cu))
+								break;  // nothing left in this block, enough pairs, or the first strip was not used up
+							const unsigned okm = __ballot_sync(0xffffffffu, ok[u]);
+							const int navail = __popc(okm);
+							const int take = min(navail, N - produced);
+							const int rank = __popc(okm & lt);
+							if (ok[u] && rank < take) {
+								const int k = produced + rank;
+								raw1[k] = x1[u];
+								raw2[k] = x2[u];
+								rawr[k] = r2[u];
+							}
+							// candidates up to the last pair taken are consumed; rejected ones behind it would be rejected
+							// again by the next draw, so a fully used strip may be skipped as a whole
+							if (take == navail)
+								pos += 4 * min(32, CANDIDATES - cu);
+							else
+								pos += 4 * ((int)__fns(okm, 0, take) + 1);
+							produced += take;
 						}
-						// candidates up to the last pair taken are consumed; rejected ones behind it would be rejected
-						// again by the next draw, so a fully used strip may be skipped as a whole
-						if (take == navail)
-							pos += 4 * min(32, CANDIDATES - c0);
-						else
-							pos += 4 * ((int)__fns(okm, 0, take) + 1);
-						produced += take;
 					}
 					__syncwarp();
+					JSDE_SUBMARK(9);
 					// pass 2: f = scale*sqrt(-2*log(r2)/r2), DW = x1*f, DZ = x2*f (random_numbers.c:127-129), bridge, sums
 					constexpr int GROUP = 4;
 					for (int k0 = lane; k0 < N; k0 += 32 * GROUP) {
@@ -626,16 +685,26 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 							for (int u = 0; u < GROUP; u++)
 								f[u] = scale * sqrt(__ddiv_rn(__dmul_rn(-2.0, lg[u]), r2[u]));
 						}
+						// all loads of the group (the item being bridged, the partial sums) before any store, see the scan above
+						double w1[GROUP], z1[GROUP], aw[GROUP], az[GROUP];
+#pragma unroll
+						for (int u = 0; u < GROUP; u++) {
+							const int k = k0 + 32 * u;
+							const bool in = k < N;
+							w1[u] = (in && bridging) ? qw[(s1 * 2 + 0) * N + k] : 0.0;
+							z1[u] = (in && bridging) ? qw[(s1 * 2 + 1) * N + k] : 0.0;
+							aw[u] = (in && started) ? sW[k] : 0.0;
+							az[u] = (in && started) ? sZ[k] : 0.0;
+						}
 #pragma unroll
 						for (int u = 0; u < GROUP; u++) {
 							const int k = k0 + 32 * u;
 							if (k < N) {
 								double gw = x1[u] * f[u], gz = x2[u] * f[u];
 								if (bridging) {
-									const double w1 = qw[(s1 * 2 + 0) * N + k], z1 = qw[(s1 * 2 + 1) * N + k];
-									const double w2 = gw + w1 * factor, z2 = gz + z1 * factor;
-									gw = w1 - w2;
-									gz = z1 - z2;
+									const double w2 = gw + w1[u] * factor, z2 = gz + z1[u] * factor;
+									gw = w1[u] - w2;
+									gz = z1[u] - z2;
 									raw1[k] = w2;
 									raw2[k] = z2;
 									qw[(s1 * 2 + 0) * N + k] = gw;
@@ -644,12 +713,13 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 									raw1[k] = gw;
 									raw2[k] = gz;
 								}
-								sW[k] = started ? sW[k] + gw : gw;
-								sZ[k] = started ? sZ[k] + gz : gz;
+								sW[k] = started ? aw[u] + gw : gw;
+								sZ[k] = started ? az[u] + gz : gz;
 							}
 						}
 					}
 					__syncwarp();
+					JSDE_SUBMARK(10);
 					if (lane == 0) {
 						if (bridging) {  // relink: the new second part goes right behind the cursor
 							for (int d = count; d > cur + 1; d--)
@@ -685,6 +755,7 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 			}
 		}
 		__syncthreads();
+		JSDE_MARK(0);
 		if (wm.mode == WIDE_PIN) {  // pin_noise (template:252-267): the appended item becomes the current one, nothing else happens
 			if (tid < T && ts[tid].running) {
 				TrajShared &S = ts[tid];
@@ -715,6 +786,7 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 			}
 			__syncthreads();
 		}
+		JSDE_MARK(1);
 
 		for (int stage = 0; stage < 2; stage++) {
 			if (UNITS > 0) {
@@ -723,6 +795,7 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 				else
 					coupling_dispatch<T, UNITS>(active, Model::coupling_table(), SC, tid);
 			}
+			JSDE_MARK(2 + 2 * stage);
 			if (stage == 0) {
 				// ---- P3: first stage (template:468-481) ----------------------------------------------------------------
 				int col = 0;
@@ -731,28 +804,43 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 					const int64_t b = b0 + tr;
 					const double *Y = e.y + b * N;
 					const double t = ts[tr].t, h = ts[tr].h;
+					// results of the thread's CPT components first, stores afterwards: nothing that could alias stands between
+					// the components' loads, so they are in flight together.  (A component-major order — one component for all
+					// trajectories of the block at a time — was measured too: 20 % slower in these phases.)
+					double fh1v[CPT], av[CPT], aAv[CPT], aBv[CPT];
 #pragma unroll
 					for (int cc = 0; cc < CPT; cc++) {
 						const int i = cc * WBLOCK + tid;
+						fh1v[cc] = av[cc] = aAv[cc] = aBv[cc] = 0.0;
 						if (i < N) {
 							const double cs = (UNITS > 0 && i < UNITS) ? SC[i * TPAD + col] : 0.0;
 							const double I10 = (e.sW[b * N + i] + e.sZ[b * N + i] * (1. / 1.7320508075688772)) * (h / 2.);
 							const double fh1 = Model::drift_local(i, t, Y, e.par, cs) * h;
-							double a;
 							if constexpr (Model::ADDITIVE) {
 								const double g1 = Model::diffusion_component(i, t + h, Y, e.par);
-								a = Y[i] + 0.75 * fh1 + 0.5 * g1 * I10 / h;
+								av[cc] = Y[i] + 0.75 * fh1 + 0.5 * g1 * I10 / h;
 							} else {  // SRIW1 (template:417-438): the arguments of fh2, g2 and g3 only need fh1 and g1
 								const double g1 = Model::diffusion_component(i, t, Y, e.par);
 								const double sqh = sqrt(h);
-								a = Y[i] + 0.75 * fh1 + 1.5 * g1 * I10 / h;
-								e.argA[b * N + i] = Y[i] + 0.25 * fh1 + 0.5 * g1 * sqh;
-								e.argB[b * N + i] = Y[i] + fh1 - g1 * sqh;
+								av[cc] = Y[i] + 0.75 * fh1 + 1.5 * g1 * I10 / h;
+								aAv[cc] = Y[i] + 0.25 * fh1 + 0.5 * g1 * sqh;
+								aBv[cc] = Y[i] + fh1 - g1 * sqh;
 							}
-							e.sF1[b * N + i] = fh1;
-							e.arg[b * N + i] = a;
+							fh1v[cc] = fh1;
+						}
+					}
+#pragma unroll
+					for (int cc = 0; cc < CPT; cc++) {
+						const int i = cc * WBLOCK + tid;
+						if (i < N) {
+							if constexpr (!Model::ADDITIVE) {
+								e.argA[b * N + i] = aAv[cc];
+								e.argB[b * N + i] = aBv[cc];
+							}
+							e.sF1[b * N + i] = fh1v[cc];
+							e.arg[b * N + i] = av[cc];
 							if (UNITS > 0 && i < UNITS)
-								SC[i * TPAD + col] = a;  // this thread's own cell: read above, rewritten here
+								SC[i * TPAD + col] = av[cc];  // this thread's own cell: read above, rewritten here
 						}
 					}
 				}
@@ -765,16 +853,25 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 						const double *Y = e.y + b * N;
 						const double t = ts[tr].t, h = ts[tr].h;
 						const double sqh = sqrt(h);
+						double g2v[CPT], g3v[CPT], aCv[CPT];
+#pragma unroll
+						for (int cc = 0; cc < CPT; cc++) {
+							const int i = cc * WBLOCK + tid;
+							g2v[cc] = g3v[cc] = aCv[cc] = 0.0;
+							if (i < N) {
+								const double g1 = Model::diffusion_component(i, t, Y, e.par);
+								g2v[cc] = Model::diffusion_component(i, t + 0.25 * h, e.argA + b * N, e.par);
+								g3v[cc] = Model::diffusion_component(i, t + h, e.argB + b * N, e.par);
+								aCv[cc] = Y[i] + 0.25 * e.sF1[b * N + i] + sqh * (-5 * g1 + 3 * g2v[cc] + 0.5 * g3v[cc]);
+							}
+						}
 #pragma unroll
 						for (int cc = 0; cc < CPT; cc++) {
 							const int i = cc * WBLOCK + tid;
 							if (i < N) {
-								const double g1 = Model::diffusion_component(i, t, Y, e.par);
-								const double g2 = Model::diffusion_component(i, t + 0.25 * h, e.argA + b * N, e.par);
-								const double g3 = Model::diffusion_component(i, t + h, e.argB + b * N, e.par);
-								e.sG2[b * N + i] = g2;
-								e.sG3[b * N + i] = g3;
-								e.argC[b * N + i] = Y[i] + 0.25 * e.sF1[b * N + i] + sqh * (-5 * g1 + 3 * g2 + 0.5 * g3);
+								e.sG2[b * N + i] = g2v[cc];
+								e.sG3[b * N + i] = g3v[cc];
+								e.argC[b * N + i] = aCv[cc];
 							}
 						}
 					}
@@ -789,9 +886,11 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 					const double t = ts[tr].t, h = ts[tr].h;
 					const double t_mid = t + 0.75 * h;
 					double worst = 0.0;
+					double nyv[CPT], erv[CPT];
 #pragma unroll
 					for (int cc = 0; cc < CPT; cc++) {
 						const int i = cc * WBLOCK + tid;
+						nyv[cc] = erv[cc] = 0.0;
 						if (i < N) {
 							const double cs = (UNITS > 0 && i < UNITS) ? SC[i * TPAD + col] : 0.0;
 							const double W = e.sW[b * N + i];
@@ -825,15 +924,23 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 							}
 							const double E_D = (fh2 - fh1) / 6;
 							const double er = fabs(E_D) + fabs(E_N);
-							e.sNY[b * N + i] = ny;
-							if (wm.mode == WIDE_PROPOSE)
-								e.sErr[b * N + i] = er;  // get_p is a separate call there (template:502-526)
+							nyv[cc] = ny;
+							erv[cc] = er;
 							const double tol = c.atol + c.rtol * fabs(ny);  // get_p (template:502-526)
 							if (er != 0.0 || tol != 0.0) {
 								const double x = er / tol;
 								if (x > worst)
 									worst = x;
 							}
+						}
+					}
+#pragma unroll
+					for (int cc = 0; cc < CPT; cc++) {
+						const int i = cc * WBLOCK + tid;
+						if (i < N) {
+							e.sNY[b * N + i] = nyv[cc];
+							if (wm.mode == WIDE_PROPOSE)
+								e.sErr[b * N + i] = erv[cc];  // get_p is a separate call there (template:502-526)
 						}
 					}
 #pragma unroll
@@ -846,6 +953,7 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 				}
 			}
 			__syncthreads();
+			JSDE_MARK(3 + 2 * stage);
 		}
 
 		// ---- P6: controller (_jitcsde.py:581-595) and commit bookkeeping, one warp per trajectory ----------------------
@@ -917,17 +1025,27 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 		}
 		__syncthreads();
 
+		JSDE_MARK(6);
 		// ---- P7: commit the accepted proposals ---------------------------------------------------------------------------
 		for (int tr = 0; tr < T; tr++) {
 			if (!ts[tr].accept)
 				continue;
 			const int64_t b = b0 + tr;
 			const int slot = ts[tr].sample_slot;
-			for (int i = tid; i < N; i += WBLOCK) {
-				const double v = e.sNY[b * N + i];
-				e.y[b * N + i] = v;
-				if (slot >= 0)
-					grid_out[((int64_t)slot * e.B + b) * N + i] = v;
+			double v[CPT];
+#pragma unroll
+			for (int cc = 0; cc < CPT; cc++) {
+				const int i = cc * WBLOCK + tid;
+				v[cc] = i < N ? e.sNY[b * N + i] : 0.0;
+			}
+#pragma unroll
+			for (int cc = 0; cc < CPT; cc++) {
+				const int i = cc * WBLOCK + tid;
+				if (i < N) {
+					e.y[b * N + i] = v[cc];
+					if (slot >= 0)
+						grid_out[((int64_t)slot * e.B + b) * N + i] = v[cc];
+				}
 			}
 		}
 		__syncthreads();
@@ -936,7 +1054,18 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 			ts[tid].sample_slot = -1;
 		}
 		__syncthreads();
+		JSDE_MARK(7);
+#ifdef JSDE_WIDE_TIMING
+		ph_rounds++;
+#endif
 	}
+#ifdef JSDE_WIDE_TIMING
+	if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 100))
+		printf("block %d: %d rounds; cycles per round: P1 %lld (trajectory 0: scan %lld, draw pass 1 %lld, pass 2 %lld) | stage-in %lld | coupling1 %lld | P3 %lld | coupling2 %lld | P5 %lld | P6 %lld | P7 %lld\n",
+			blockIdx.x, ph_rounds, ph[0] / max(ph_rounds, 1), ph[8] / max(ph_rounds, 1), ph[9] / max(ph_rounds, 1), ph[10] / max(ph_rounds, 1),
+			ph[1] / max(ph_rounds, 1), ph[2] / max(ph_rounds, 1), ph[3] / max(ph_rounds, 1),
+			ph[4] / max(ph_rounds, 1), ph[5] / max(ph_rounds, 1), ph[6] / max(ph_rounds, 1), ph[7] / max(ph_rounds, 1));
+#endif
 
 	// ---- store ----------------------------------------------------------------------------------------------------
 	if (warp < live) {
