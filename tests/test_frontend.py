@@ -174,3 +174,29 @@ def test_irregular_large_systems_are_refused_with_a_reason():
 	fs = [-(1.0 + float(rng.random())) * y(i) ** (2 + i % 3) - float(rng.random()) * y((i * 7 + 3) % n) ** 2 for i in range(n)]
 	with pytest.raises(NotImplementedError, match="structural templates"):
 		spec_from_symbolic(fs, [0.1] * n)
+
+
+def test_jump_randomness_is_renewed_on_reset_unless_given_explicitly():
+	"""reference: IJI and amp draw from a live generator, so a reset instance gives an independent sample; here the tape is
+	redrawn (callable IJI, implicit xis) and the generated mode takes a new seed — explicit arrays and seeds are replayed"""
+	amp = [0.5 * xi]
+	rng = np.random.default_rng(0)
+	A = jitcsde_jump(lambda time, state: rng.exponential(1.0), amp, [-y(0)], [0.1], rng=np.random.default_rng(1), ensemble=4, tape_length=8, verbose=False)
+	A._make_tape()
+	first = (A._taus.copy(), A._xis.copy())
+	A.set_initial_value([1.0], 0.0)  # -> reset_integrator
+	assert A._taus is None and not A._tape_uploaded
+	A._make_tape()
+	assert not np.array_equal(A._taus, first[0]) and not np.array_equal(A._xis, first[1])
+	taus, xis = np.full((4, 3), 0.5), np.zeros((4, 3))
+	B = jitcsde_jump(taus, amp, [-y(0)], [0.1], xis=xis, ensemble=4, verbose=False)
+	B._make_tape()
+	B.set_initial_value([1.0], 0.0)
+	assert B._taus is not None and np.array_equal(B._taus, taus)
+	C = jitcsde_jump("generated", amp, [-y(0)], [0.1], rng=np.random.default_rng(2), ensemble=4, verbose=False)
+	s1 = C._generated_seed()
+	C.set_initial_value([1.0], 0.0)
+	assert C._generated_seed() != s1
+	D = jitcsde_jump("generated", amp, [-y(0)], [0.1], jump_seed=99, ensemble=4, verbose=False)
+	D.set_initial_value([1.0], 0.0)
+	assert D._generated_seed() == 99

@@ -147,3 +147,21 @@ def test_generated_jumps_with_a_rate_through_the_public_api():
 	assert_bits_equal(a, b, "same jump seed")
 	assert not np.array_equal(a, c)
 	assert ja == jb and abs(ja - 256 * 5.0 * 4.0) < 5 * np.sqrt(256 * 5.0 * 4.0)  # Poisson(rate 4 per unit time)
+
+
+def test_compile_options_cse_and_simplify_on_the_device():
+	"""compile_C(do_cse=True) / (simplify=True) regenerate the model; the device runs exactly the regenerated expressions
+	(bit-identical to the oracle's build of the same body)"""
+	fs = [sympy.sin(y(0) * y(1)) * 0 + y(1) * y(0) - y(0), -(y(0) * y(1)) - 0.5 * y(1)]
+	gs = [0.1 * y(0) * y(1), 0.2 + 0.1 * y(0) * y(1)]
+	y0 = np.random.default_rng(4).random((32, 2))
+	for kwargs in ({"do_cse": True}, {"simplify": True}):
+		SDE = jitcsde(fs, gs, ensemble=32, verbose=False)
+		SDE.compile_C(**kwargs)
+		SDE.set_seed(0)
+		SDE.set_initial_value(y0, 0.0)
+		out = SDE.integrate(0.5)
+		if "do_cse" in kwargs:
+			assert "cse_d0" in SDE.spec.f_body
+		ref = port.run_ensemble(SDE.spec, y0, np.arange(32, dtype=np.uint32), 0.0, 0.5)
+		assert_bits_equal(out, ref["y"], str(kwargs))
