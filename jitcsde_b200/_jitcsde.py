@@ -17,6 +17,7 @@ What is different from the reference, and why:
 
 from __future__ import annotations
 
+import os
 import random
 from warnings import warn
 
@@ -59,8 +60,11 @@ class jitcsde:
 			ensemble=1, device=0, noise_capacity=0, spec: ModelSpec | None = None, coupling="exact", _jump_amp=None, _jump_iji=None):
 		if callback_functions:
 			raise NotImplementedError("Python callbacks cannot run inside a GPU kernel; express the term symbolically.")
+		saved_library = None
 		if module_location is not None and spec is None:
-			raise NotImplementedError("module_location is not supported; pass spec= (a ModelSpec) to reuse printed code.")
+			spec, saved_library = self._load_compiled(module_location)
+			if n is not None and int(n) != spec.n:
+				raise ValueError(f"the saved module has {spec.n} components, not n = {n}")
 		self.verbose = verbose
 		self.B = int(ensemble)
 		if self.B < 1:
@@ -93,6 +97,9 @@ class jitcsde:
 		self._parameters = None
 		self.compile_attempt = None
 		self.last_stats = None
+		if saved_library is not None:
+			self._library = saved_library
+			self.compile_attempt = True
 
 	def _make_spec(self, simplify=None, do_cse=False):
 		a = self._symbolic
@@ -213,6 +220,52 @@ class jitcsde:
 		return self._library
 
 	compile_cuda = compile_C
+
+	#: suffix of saved modules (the reference enforces the platform's extension-module suffix, jitcxde_common)
+	MODULE_SUFFIX = ".jsde"
+
+	def save_compiled(self, destination="", overwrite=False):
+		"""
+		Saves the compiled model for later use with `module_location=` (reference: `jitcxde.save_compiled`, used by
+		tests/test_jitcsde.py:65-68).  The file is an archive of the printed model (ModelSpec, JSON) and the sm_100a
+		library built from it; a directory or "" as destination gets the default file name.  Returns the path.
+		"""
+		import zipfile
+		if self.compile_attempt is None:
+			self.compile_C()
+		default = f"jitced_{self.spec.name}{self.MODULE_SUFFIX}"
+		if destination == "":
+			destination = default
+		elif os.path.isdir(destination) or destination.endswith(os.sep):
+			destination = os.path.join(destination, default)
+		elif not destination.endswith(self.MODULE_SUFFIX):
+			destination = os.path.splitext(destination)[0] + self.MODULE_SUFFIX
+		if os.path.exists(destination) and not overwrite:
+			raise OSError("Target File already exists and \"overwrite\" is set to False")
+		os.makedirs(os.path.dirname(os.path.abspath(destination)), exist_ok=True)
+		with zipfile.ZipFile(destination, "w", zipfile.ZIP_DEFLATED) as z:
+			z.writestr("spec.json", self.spec.to_json())
+			z.writestr("sources_digest", _build._sources_digest())
+			z.write(self._library, "library.so")
+		return destination
+
+	@staticmethod
+	def _load_compiled(location):
+		"""-> (ModelSpec, path of the installed library or None).  The saved binary is used when it was built from the
+		kernel sources of this installation; otherwise the model is rebuilt from its printed form on first use."""
+		import zipfile
+		with zipfile.ZipFile(location) as z:
+			spec = ModelSpec.from_json(z.read("spec.json").decode())
+			if z.read("sources_digest").decode() != _build._sources_digest():
+				return spec, None
+			target = _build.library_path(spec)
+			if not os.path.isfile(target):
+				os.makedirs(os.path.dirname(target), exist_ok=True)
+				tmp = f"{target}.{os.getpid()}.tmp"
+				with open(tmp, "wb") as fh:
+					fh.write(z.read("library.so"))
+				os.replace(tmp, target)
+		return spec, target
 
 	def generate_lambdas(self):
 		raise NotImplementedError("There is no Python/CPU core in this implementation (no fallback by design).")

@@ -16,7 +16,9 @@ bit-for-bit parity possible for polynomial/rational models (SURVEY.md §7.3 item
 
 from __future__ import annotations
 
+import dataclasses
 import hashlib
+import json
 from dataclasses import dataclass, field
 
 
@@ -95,6 +97,21 @@ JSDE_MODEL_FN double jsde_coupling_sum(int i, const double *Y)
 			assert len(self.f) == self.n, "len(f) != n"
 		if not self.g_body:
 			assert len(self.g) == self.n, "len(g) != n"
+
+	def to_json(self) -> str:
+		"""every field as stored (for wide models: after __post_init__ has completed preamble and bodies)"""
+		return json.dumps(dataclasses.asdict(self))
+
+	@classmethod
+	def from_json(cls, text: str) -> "ModelSpec":
+		"""inverse of to_json; does not run __post_init__ again (it would append the wide-model helpers twice)"""
+		d = json.loads(text)
+		jump = d.pop("jump")
+		self = object.__new__(cls)
+		for key, value in d.items():
+			object.__setattr__(self, key, tuple(value) if isinstance(value, list) else value)
+		object.__setattr__(self, "jump", JumpSpec(tuple(jump["amp"]), jump["iji"]) if jump else None)
+		return self
 
 	def digest(self) -> str:
 		h = hashlib.sha256()
