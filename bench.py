@@ -323,8 +323,8 @@ def run_gpu_arm(args):
 	wall = time.perf_counter() - t0
 	clocks = sampler.stop() if rank == 0 else None
 	# kernels launched per step: set_integration_parameters (fill dt) + set_state (rows->cols, fill t) + seed (once, lazily) +
-	# integrate + get_state (cols->rows) [+ moments]
-	launches = args.steps * (6 + (1 if world > 1 else 0))
+	# integrate (pool of waiting trajectories + the integrate kernel) + get_state (cols->rows) [+ moments]
+	launches = args.steps * (7 + (1 if world > 1 else 0))
 	failed = stats["n_min_step"] + stats["n_overflow"]
 	(accepted, rejected, failed), (kernel_ms, wall) = over_ranks([accepted, rejected, failed], [kernel_ms, wall])
 	weak_value = accepted / (kernel_ms * 1e-3)

@@ -175,7 +175,7 @@ class Ensemble:
 			pass
 
 	def set_option(self, name: str, value) -> None:
-		"""`jsde_set_option`: "coupling" = "exact" | "dmma" (wide models), "recycle" = 0 | 1 (lane models)"""
+		"""`jsde_set_option`: "coupling" = "exact" | "dmma" (wide models), "recycle" = 0 | 1 and "slice" = rounds between yields (lane models)"""
 		self._check(self.lib.jsde_set_option(self._h, name.encode(), str(value).encode()))
 
 	# ---- state / seed / parameters --------------------------------------------------------------------------------

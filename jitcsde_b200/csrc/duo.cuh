@@ -29,11 +29,13 @@
 // launches (same spill format as WarpRng, which the single-step kernels use).
 //
 // Trajectory recycling (kernels.cuh, RECYCLE): the grid is at most one wave of blocks; a lane whose trajectory is done
-// takes the next one from a pool (atomic counter) instead of idling until its warp's and block's slowest trajectory
+// takes the next one from a pool instead of idling until its warp's and block's slowest trajectory
 // finishes (+26 % on SRI-Lorenz, whose step counts differ by tens of per cent between trajectories).  The consumer
 // announces the change through `swap[lane]` together with the final popped count of the old trajectory; the producer
 // then spills the old trajectory's queued pairs and stream position, loads the new one's, and refills — the lane sits
-// out that one round.  Every lane's first trajectory arrives the same way (round 0).
+// out that one round.  Every lane's first trajectory arrives the same way (round 0).  `swap = -2` releases the current
+// trajectory without taking another (first half of a yield: kernels.cuh).  The published mask holds the lanes that keep the
+// warp pair alive: lanes that step, that have a trajectory to hand back, or that are in the middle of a yield.
 #pragma once
 
 #include "warp_rng.cuh"
@@ -318,11 +320,16 @@ struct PairProducer {
 			lvl = (int)(pushed - L::popped(base, parity)[lane]);
 			const int next = L::swap(base, parity)[lane];
 			parity ^= 1;
-			if (next >= 0) {  // the consumer lane has moved on to another trajectory
+			if (next >= 0 || next == -2) {  // the consumer lane has moved on to another trajectory, or gives this one up (-2)
 				if (traj >= 0)
 					store(spill, levels, chunks, B, traj);
-				traj = next;
-				load(spill, levels, chunks, B, traj);
+				// a trajectory can change hands between SMs within a launch (kernels.cuh, yield): what this warp wrote for the
+				// old one must be visible before the consumer publishes it, and what another SM wrote for the new one before
+				// this warp reads it
+				__threadfence();
+				traj = next >= 0 ? next : -1;
+				if (traj >= 0)
+					load(spill, levels, chunks, B, traj);
 			}
 			__syncwarp();
 			if (!act)

@@ -39,7 +39,9 @@ struct CallTotals {
 	unsigned long long accepted, rejected, fresh_draws, jumps;
 	long long n_min_step, n_overflow;
 	int max_depth;
-	unsigned long long pool_taken;  // trajectories handed out beyond the grid's first wave (k_integrate recycles lanes)
+	// k_integrate with lane recycling: trajectories beyond the grid's first wave wait in EnsembleView::pool[0 .. waiting)
+	int waiting;                // shrinks when a lane whose trajectory is done pops the last one
+	unsigned long long cursor;  // rotating position of the yield exchanges
 	unsigned long long tape_exhausted;  // trajectories that wanted another jump from a tape that had none left
 };
 
@@ -69,6 +71,8 @@ struct EnsembleView {
 	unsigned long long jump_seed;
 	long long jump_first;  // global index of trajectory 0 (sharded ensembles draw the same variates as one big one)
 	CallTotals *totals;
+	int *pool;         // [B] trajectory numbers waiting for a lane (k_integrate, RECYCLE)
+	int slice_rounds;  // rounds after which a warp's lanes exchange their trajectories with waiting ones (0: never)
 };
 
 }  // namespace jsde

@@ -17,7 +17,7 @@ using namespace jsde::abi;
 
 struct jsde_handle : HandleBase {
 	int resident_blocks = 0;  // blocks of k_integrate that fit on the device at once
-	bool recycle = false;     // lanes take further trajectories from a pool (grid = one wave): see kernels.cuh
+	bool recycle = true;      // lanes take further trajectories from a pool (grid = one wave): see kernels.cuh
 	EnsembleView v{};
 	double *staging = nullptr;  // [B][max(n,1)] doubles: host-layout buffer for transposes and per-trajectory vectors
 	double *par_rows = nullptr, *par_cols = nullptr;  // per-trajectory control parameters (allocated on first use)
@@ -101,6 +101,7 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	ALLOC(v.status, B); ALLOC(v.accepted, B); ALLOC(v.rejected, B);
 	ALLOC(v.next_jump, B); ALLOC(v.jump_set, B); ALLOC(v.tape_pos, B);
 	ALLOC(v.totals, 1);
+	ALLOC(v.pool, B);
 	ALLOC(h->seeds, B);
 	ALLOC(h->par, Model::NPAR > 0 ? Model::NPAR : 1);
 	ALLOC(h->staging, B * (n > 1 ? n : 1));
@@ -140,11 +141,15 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_integrate<Model, false, true>, DUO_BLOCK, duo_smem) == cudaSuccess &&
 			cudaGetDeviceProperties(&prop, device) == cudaSuccess && per_sm > 0)
 			h->resident_blocks = per_sm * prop.multiProcessorCount;
-		h->recycle = !Model::ADDITIVE;
+		h->recycle = true;
 		if (const char *env = getenv("JSDE_RECYCLE"))
 			h->recycle = atoi(env) != 0;
 		if (const char *env = getenv("JSDE_RESIDENT_BLOCKS"))  // test knob: a tiny grid makes small ensembles recycle lanes
 			if (atoi(env) > 0) h->resident_blocks = atoi(env);
+		// rounds (attempted steps) between two yields of a warp's lanes; ~18 ms of a full GPU's time at the default
+		v.slice_rounds = 4096;
+		if (const char *env = getenv("JSDE_SLICE"))
+			if (atoi(env) >= 0) v.slice_rounds = atoi(env);
 	}
 	*out = h;
 	return JSDE_OK;
@@ -165,6 +170,14 @@ int jsde_set_option(jsde_t *h, const char *name, const char *value)
 		return fail(JSDE_E_ARG, "Wrong input.");
 	if (!strcmp(name, "recycle") && (!strcmp(value, "0") || !strcmp(value, "1"))) {
 		h->recycle = value[0] == '1';
+		return JSDE_OK;
+	}
+	if (!strcmp(name, "slice")) {  // rounds between yields of recycled lanes; 0: trajectories never change hands unfinished
+		char *end = nullptr;
+		const long rounds = strtol(value, &end, 10);
+		if (end == value || *end || rounds < 0 || rounds > 0x7fffffffL)
+			return fail(JSDE_E_ARG, "Wrong input. (slice: a number of rounds >= 0)");
+		h->v.slice_rounds = (int)rounds;
 		return JSDE_OK;
 	}
 	if (!strcmp(name, "coupling") && !strcmp(value, "exact"))
@@ -297,6 +310,8 @@ static int integrate_common(jsde_t *h, double target_time, int use_tape, jsde_st
 	if (h->recycle && h->resident_blocks > 0 && all_blocks > (unsigned)h->resident_blocks) {
 		// one wave of blocks: lanes take further trajectories from a pool as theirs finish (kernels.cuh)
 		const unsigned grid = (unsigned)h->resident_blocks;
+		const int64_t first_wave = (int64_t)grid * 32 * DUO_PAIRS;
+		k_pool_init<<<grid_for(h->B - first_wave, 256), 256, 0, h->stream>>>(h->v.pool, (int)first_wave, (int)(h->B - first_wave), h->v.totals);
 		if (grid_times_dev)
 			k_integrate<Model, true, true><<<grid, DUO_BLOCK, duo_smem_bytes<Model>(), h->stream>>>(h->v, h->ctrl, target_time, use_tape,
 				grid_times_dev, grid_count, grid_out_dev);

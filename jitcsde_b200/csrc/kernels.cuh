@@ -52,15 +52,30 @@ __device__ __forceinline__ ModelRng<Model> make_rng(const EnsembleView &e, int64
 template <class Model>
 constexpr size_t duo_smem_bytes() { return ((size_t)DUO_PAIRS * PairLayout<Model::N>::DOUBLES + MATH_TAB_DOUBLES) * sizeof(double); }
 
-// RECYCLE: the grid is one wave of blocks and a lane whose trajectory is done takes the next one from a pool.  Pays when
-// the trajectories' step counts differ a lot (multiplicative noise: +26 % on SRI-Lorenz to t = 10); costs ~2 % cycles
-// and, under the power cap, ~2 % clock when they do not (additive Lorenz to t = 100: step counts within 1 %), so the
-// host enables it for non-additive models (JSDE_RECYCLE=0/1 overrides).
+// RECYCLE: the grid is one wave of blocks and the trajectories beyond it wait in a pool (e.pool: a compact array of
+// trajectory numbers, CallTotals::waiting of them).  A lane whose trajectory is done pops the last waiting one; and every
+// `e.slice_rounds` rounds a warp's lanes *yield*: each exchanges its unfinished trajectory with a waiting one (atomicExch at
+// a rotating position), so that all trajectories advance at the same average pace and finish together — without that, an
+// ensemble of 2.3 times the resident lanes (2^20 trajectories split over 8 GPUs) takes three trajectory lengths instead of
+// 2.3.  Measured (profiles/r02_time_slicing_ab.log; same box, bit-identical results in every setting): additive Lorenz,
+// 2^17 trajectories to t = 100: 1.07e10 (plain grid) / 1.04e10 (pool only) -> 1.15e10 accepted steps/s; 2^20 trajectories:
+// 1.16e10 / 1.11e10 -> 1.17e10; SRI-Lorenz 2^20 to t = 10: 5.57e9 / 6.58e9 -> 6.78e9.  The pool alone pays when the
+// trajectories' step counts differ a lot (multiplicative noise) and costs a few per cent when they do not (fuller warps,
+// lower clock under the power cap); with time slicing it is the default for every model (JSDE_RECYCLE=0/1, JSDE_SLICE and
+// jsde_set_option("recycle" | "slice") override).
+//
+// A yield takes three passes of the (cold) outer loop, because the trajectory's generator-side state is written by the
+// producer warp: pass 1 hands the stepper state back and announces the release (swap = -2); the producer spills queue
+// and stream position during the following round; pass 3, two rendezvous later, publishes the trajectory number with
+// the exchange and takes the other one.  __threadfence on both sides of the exchange makes the state written by one
+// SM's consumer and producer visible to the SM that continues the trajectory.  Exchanges conserve trajectory numbers
+// whatever the interleaving: a lane that finds a slot emptied by a concurrent pop (-1) takes its deposit back.
 template <class Model, bool GRID, bool RECYCLE>
 __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE>::BLOCKS) k_integrate(EnsembleView e, Controller c, double target, int use_tape,
 	const double *__restrict__ grid_times_, int grid_count, double *__restrict__ grid_out)
 {
 	constexpr int N = Model::N;
+	constexpr bool SLICED = RECYCLE && !GRID;  // a yielded trajectory would have to carry its sample index along
 	extern __shared__ __align__(16) double jsde_smem[];
 	stage_math_tables(jsde_smem);
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,10 +97,17 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE
 	// examples/noisy_lorenz.py:95-96 (truncated last step + Brownian bridge at every sample time), in one launch.
 	PairConsumer<N, rng_tail<Model>> rng(pair_smem, jsde_smem, pair);
 	Lane<Model, PairConsumer<N, rng_tail<Model>>> L(e, 0, rng);
-	// This lane starts with the trajectory of its global index and (RECYCLE) takes the next one from the pool whenever
-	// its trajectory is done (duo.cuh).  Results do not depend on which lane integrates a trajectory.
+	// This lane starts with the trajectory of its global index and (RECYCLE) goes on with trajectories from the pool.
+	// Results do not depend on which lane integrates a trajectory, nor on how often it changes hands.
 	int k = -1;  // B < 2^31 (jsde_create)
 	int upcoming = (int)min((int64_t)0x7fffffff, ((int64_t)blockIdx.x * DUO_PAIRS + pair) * 32 + lane);
+	if (upcoming >= e.B)
+		upcoming = -1;
+	bool seeking = false;   // RECYCLE: no trajectory, but the pool may still have one
+	int held = -1;          // SLICED: the trajectory this lane is giving up (not yet published)
+	int yield_phase = 0;    // SLICED: 0 none, 1 released (the producer is spilling), 2 ready for the exchange
+	bool yielding = false;
+	int rounds_left = SLICED && e.slice_rounds > 0 ? e.slice_rounds : 0x7fffffff;  // warp-uniform
 	unsigned acc = 0, rej = 0, jumps = 0;  // per call and trajectory: far below 2^32 (the noise memory would overflow first)
 	int grid_index = 0;
 	double cur_target = target;  // differs from `target` only in sampling-grid mode
@@ -96,61 +118,93 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE
 	bool need_target = true, to_jump = false;
 	double tgt = target;
 	bool primed = false;  // round 0 is empty: the producer fills the FIFOs for the first time
-	// Two nested loops: the inner one is the hot round loop; the outer one (cold) hands finished trajectories back and
-	// takes new ones, so that its register needs do not shape the allocation of the hot loop.
+	// Two nested loops: the inner one is the hot round loop; the outer one (cold) hands trajectories back and takes new
+	// ones, so that its register needs do not shape the allocation of the hot loop.
 	bool finished = false;
 	while (!finished) {
-		int next_trajectory = -1;
-		if (!active && upcoming >= 0) {
-			if (k >= 0) {  // hand back the finished trajectory
-				L.store();
-				if (Model::HAS_JUMP && use_tape) {
-					e.next_jump[k] = next_jump;
-					e.jump_set[k] = jump_set ? 1 : 0;
-					e.tape_pos[k] = tape_pos;
-				}
-				e.accepted[k] += acc;
-				e.rejected[k] += rej;
-				CallTotals *tot = e.totals;  // once per trajectory: cheaper than carrying running sums in registers
-				if (acc) atomicAdd(&tot->accepted, (unsigned long long)acc);
-				if (rej) atomicAdd(&tot->rejected, (unsigned long long)rej);
-				if (L.fresh) atomicAdd(&tot->fresh_draws, (unsigned long long)L.fresh);
-				if (jumps) atomicAdd(&tot->jumps, (unsigned long long)jumps);
-				if (Model::HAS_JUMP && exhausted) atomicAdd(&tot->tape_exhausted, 1ull);
-				if (L.status == TRAJ_MIN_STEP) atomicAdd((unsigned long long *)&tot->n_min_step, 1ull);
-				if (L.status == TRAJ_NOISE_OVERFLOW) atomicAdd((unsigned long long *)&tot->n_overflow, 1ull);
-				if (L.max_depth) atomicMax(&tot->max_depth, L.max_depth);
-				upcoming = RECYCLE ? (int)min(0x7fffffffull, (unsigned long long)gridDim.x * (DUO_PAIRS * 32) + atomicAdd(&tot->pool_taken, 1ull)) : -1;
-				k = -1;
+		int next_trajectory = -1;  // what the producer is told: >= 0 switch to that trajectory, -2 release the current one
+		CallTotals *tot = e.totals;
+		if (SLICED && yield_phase == 2) {  // the producer has spilled `held`: publish it and take another
+			int got = held;
+			__threadfence();
+			const int waiting = *(volatile int *)&tot->waiting;
+			if (waiting > 0) {
+				const int p = (int)(atomicAdd(&tot->cursor, 1ull) % (unsigned long long)waiting);
+				got = atomicExch(&e.pool[p], held);
+				if (got < 0)  // a concurrent pop has just emptied this slot: take the deposit (or a racer's) back
+					got = atomicExch(&e.pool[p], -1);
 			}
-			if (upcoming >= 0 && upcoming < e.B) {  // take the next trajectory; this lane sits out the round in which its queue is rebuilt
-				k = upcoming;
-				next_trajectory = k;
-				L.rebind(k);
-				L.load();
-				if (L.status == TRAJ_MIN_STEP)
-					L.status = TRAJ_OK;  // the reference raises once per call and lets the caller carry on (:569-579)
-				L.cursor = 0;
-				L.fresh = 0;
-				L.max_depth = 0;
-				acc = rej = jumps = 0;
-				exhausted = false;
-				if (Model::HAS_JUMP && use_tape) {
-					next_jump = e.next_jump[k];
-					jump_set = e.jump_set[k] != 0;
-					tape_pos = e.tape_pos[k];
-				}
-				grid_index = 0;
-				cur_target = grid_times ? grid_times[0] : target;
-				need_target = true;
-				to_jump = false;
-				active = L.status == TRAJ_OK;  // a trajectory that cannot run is handed back in the next round
-				sit_out = true;
+			__threadfence();
+			held = -1;
+			yield_phase = 0;
+			upcoming = got;
+			seeking = got < 0;
+		} else if (SLICED && yield_phase == 1)
+			yield_phase = 2;
+		else if (!active && k >= 0) {  // hand back: the trajectory is done (or failed), or this lane yields it
+			L.store();
+			if (Model::HAS_JUMP && use_tape) {
+				e.next_jump[k] = next_jump;
+				e.jump_set[k] = jump_set ? 1 : 0;
+				e.tape_pos[k] = tape_pos;
+			}
+			e.accepted[k] += acc;
+			e.rejected[k] += rej;
+			// once per trajectory (and slice): cheaper than carrying running sums in registers
+			if (acc) atomicAdd(&tot->accepted, (unsigned long long)acc);
+			if (rej) atomicAdd(&tot->rejected, (unsigned long long)rej);
+			if (L.fresh) atomicAdd(&tot->fresh_draws, (unsigned long long)L.fresh);
+			if (jumps) atomicAdd(&tot->jumps, (unsigned long long)jumps);
+			if (Model::HAS_JUMP && exhausted) atomicAdd(&tot->tape_exhausted, 1ull);
+			if (L.status == TRAJ_MIN_STEP) atomicAdd((unsigned long long *)&tot->n_min_step, 1ull);
+			if (L.status == TRAJ_NOISE_OVERFLOW) atomicAdd((unsigned long long *)&tot->n_overflow, 1ull);
+			if (L.max_depth) atomicMax(&tot->max_depth, L.max_depth);
+			if (SLICED && yielding) {
+				held = k;
+				yield_phase = 1;
+				next_trajectory = -2;
+				yielding = false;
 			} else
-				upcoming = -1;  // pool exhausted
+				seeking = RECYCLE;
+			k = -1;
+		}
+		if (RECYCLE && seeking) {  // pop the last waiting trajectory
+			seeking = false;
+			const int w = atomicSub(&tot->waiting, 1) - 1;
+			if (w >= 0) {
+				upcoming = atomicExch(&e.pool[w], -1);  // never empty: slots below `waiting` hold trajectories (see the exchange above)
+				__threadfence();
+			} else
+				atomicAdd(&tot->waiting, 1);  // the pool is empty: this lane is done
+		}
+		if (upcoming >= 0) {  // take the trajectory; this lane sits out the round in which its queue is rebuilt
+			k = upcoming;
+			upcoming = -1;
+			next_trajectory = k;
+			L.rebind(k);
+			L.load();
+			if (L.status == TRAJ_MIN_STEP)
+				L.status = TRAJ_OK;  // the reference raises once per call and lets the caller carry on (:569-579)
+			L.cursor = 0;
+			L.fresh = 0;
+			L.max_depth = 0;
+			acc = rej = jumps = 0;
+			exhausted = false;
+			if (Model::HAS_JUMP && use_tape) {
+				next_jump = e.next_jump[k];
+				jump_set = e.jump_set[k] != 0;
+				tape_pos = e.tape_pos[k];
+			}
+			grid_index = 0;
+			cur_target = grid_times ? grid_times[0] : target;
+			need_target = true;
+			to_jump = false;
+			active = L.status == TRAJ_OK;  // a trajectory that cannot run is handed back in the next round
+			sit_out = true;
 		}
 		while (true) {
-		if (!rng.rendezvous(active, next_trajectory)) {
+		// the warp goes on while any lane steps, holds a trajectory to hand back, or is in the middle of a yield
+		if (!rng.rendezvous(active || k >= 0 || (SLICED && yield_phase != 0), next_trajectory)) {
 			finished = true;
 			break;
 		}
@@ -262,12 +316,19 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE
 				}
 			}
 		}
-		if (__any_sync(0xffffffffu, !active && upcoming >= 0))
-			break;  // somebody has a trajectory to hand back (and perhaps one to take)
+		if (SLICED && --rounds_left == 0) {  // the warp's lanes give their trajectories up for waiting ones
+			rounds_left = e.slice_rounds;
+			if (active && !resting && *(volatile int *)&e.totals->waiting > 0) {
+				yielding = true;
+				active = false;
+			}
+		}
+		if (__any_sync(0xffffffffu, (!active && k >= 0) || (SLICED && yield_phase != 0)))
+			break;  // somebody has a trajectory to hand back (and perhaps one to take), or a yield to complete
 		}
 	}
-	// every lane has handed back its last trajectory before the loop can end: a lane with a trajectory is active or about
-	// to hand it back, and keeps `upcoming >= 0` until the pool is exhausted
+	// every lane has handed back its last trajectory before the loop can end: a lane with a trajectory (k >= 0) or a yield
+	// in progress keeps the warp alive (rendezvous), and the cold pass above is entered whenever such a lane is not stepping
 }
 
 // ---- single-step surface (reference core methods, one launch each) ---------------------------------------------

@@ -44,6 +44,18 @@ __global__ void k_cols_to_rows(const double *cols, double *rows, int64_t B, int 
 	rows[idx] = cols[(int64_t)i * B + k];
 }
 
+// lane recycling (kernels.cuh): the trajectories beyond the grid's first wave, in ascending order
+__global__ void k_pool_init(int *pool, int first, int count, CallTotals *totals)
+{
+	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx < count)
+		pool[idx] = first + (int)idx;
+	if (idx == 0) {
+		totals->waiting = count;
+		totals->cursor = 0;
+	}
+}
+
 __global__ void k_fill(double *dst, double value, int64_t count)
 {
 	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -306,13 +306,16 @@ def test_ensemble_vs_oracle(name, B, T):
 	assert stats["n_overflow"] == 0
 
 
+@pytest.mark.parametrize("slice_rounds", [0, 5, 64, 4096])
 @pytest.mark.parametrize("name,B,T", [("lorenz_additive", 1000, 0.5), ("lorenz_multiplicative", 700, 0.4), ("gbm", 999, 4.0)])
-def test_lane_recycling_small_grid(monkeypatch, name, B, T):
+def test_lane_recycling_small_grid(monkeypatch, name, B, T, slice_rounds):
 	"""k_integrate with a grid of two blocks (256 lanes): every lane integrates several trajectories one after the other,
-	handing queued generator pairs and stream positions back and forth — results must not depend on that, within one
-	call, across calls, and for the sampling grid."""
+	handing queued generator pairs and stream positions back and forth — and, with time slicing, gives unfinished
+	trajectories up for waiting ones every `slice_rounds` rounds (5: a trajectory changes hands dozens of times, between
+	warps and blocks).  Results must not depend on that, within one call, across calls, and for the sampling grid."""
 	monkeypatch.setenv("JSDE_RECYCLE", "1")
 	monkeypatch.setenv("JSDE_RESIDENT_BLOCKS", "2")
+	monkeypatch.setenv("JSDE_SLICE", str(slice_rounds))
 	spec = models.ALL[name]
 	E, y0, seeds = make(spec, B)
 	stats = E.integrate(T)
@@ -334,9 +337,11 @@ def test_lane_recycling_small_grid(monkeypatch, name, B, T):
 			assert_bits_equal(grid[j, k], P.integrate(float(tj)), f"trajectory {k} sample {j}")
 
 
-def test_lane_recycling_with_jumps(monkeypatch):
+@pytest.mark.parametrize("slice_rounds", [0, 7])
+def test_lane_recycling_with_jumps(monkeypatch, slice_rounds):
 	monkeypatch.setenv("JSDE_RECYCLE", "1")
 	monkeypatch.setenv("JSDE_RESIDENT_BLOCKS", "1")
+	monkeypatch.setenv("JSDE_SLICE", str(slice_rounds))
 	spec = models.lorenz_jumpy
 	B = 300
 	E, y0, seeds = make(spec, B)
@@ -349,6 +354,32 @@ def test_lane_recycling_with_jumps(monkeypatch):
 		P.integrate_jumps(1.0, taus[k], xis[k])
 		P.integrate_jumps(2.0, taus[k], xis[k])
 		assert_bits_equal(y[k], P.get_state(), f"trajectory {k}")
+
+
+@pytest.mark.parametrize("name,T", [("lorenz_additive", 1.0), ("lorenz_multiplicative", 0.6)])
+def test_time_slicing_across_many_blocks(monkeypatch, name, T):
+	"""2.3 waves on a grid of 40 blocks (5120 lanes, 11 800 trajectories — the shape of a 2^20 ensemble split over eight
+	GPUs): trajectories migrate between SMs every 24 rounds; every trajectory must end up exactly where the oracle puts it,
+	and the call's totals must count every step once."""
+	monkeypatch.setenv("JSDE_RECYCLE", "1")
+	monkeypatch.setenv("JSDE_RESIDENT_BLOCKS", "40")
+	monkeypatch.setenv("JSDE_SLICE", "24")
+	spec, B = models.ALL[name], 11800
+	E, y0, seeds = make(spec, B)
+	stats = E.integrate(T)
+	sample = np.arange(0, B, 59)
+	ref = port.run_ensemble(spec, y0[sample], seeds[sample], 0.0, T)
+	assert_bits_equal(E.get_state()[sample], ref["y"], name)
+	assert_bits_equal(E.t[sample], ref["t"], name + " t")
+	_, acc, rej = E.controller_state()
+	assert (acc[sample].astype(np.int64) == ref["accepted"]).all() and (rej[sample].astype(np.int64) == ref["rejected"]).all()
+	assert stats["accepted"] == int(acc.sum()) and stats["rejected"] == int(rej.sum())
+	assert (E.t == T).all()
+	# the same ensemble without slicing and without recycling: identical bits for all trajectories
+	monkeypatch.setenv("JSDE_RECYCLE", "0")
+	F, _, _ = make(spec, B)
+	F.integrate(T)
+	assert_bits_equal(E.get_state(), F.get_state(), "sliced vs plain")
 
 
 @pytest.mark.parametrize("name", ["lorenz_additive", "lorenz_multiplicative"])
