@@ -190,7 +190,9 @@ __device__ __forceinline__ void coupling_phase(const double *__restrict__ AT, do
 			acc[q][tr] = 0.0;
 		}
 	}
-#pragma unroll 4
+	// few live trajectories: little arithmetic per loaded A_ij, the loop waits for L2 — keep more loads in flight
+	constexpr int J_UNROLL = T <= 2 ? 16 : T <= 4 ? 8 : 4;
+#pragma unroll J_UNROLL
 	for (int j = 0; j < UNITS; j++) {
 		double a[IPT];
 #pragma unroll

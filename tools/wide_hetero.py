@@ -19,3 +19,6 @@ for tpb in (2, 4, 7, 8):
 	n = B // tpb * tpb
 	g = att[:n].reshape(-1, tpb)
 	print(f"  blocks of {tpb}: mean of block-max / mean = {g.max(axis=1).mean()/att.mean():.3f}; max/mean {att.max()/att.mean():.3f}")
+out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out")
+if os.path.isdir(out):
+	np.save(os.path.join(out, "wide_attempts.npy"), att)
