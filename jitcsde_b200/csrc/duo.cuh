@@ -48,24 +48,28 @@ constexpr int DUO_BLOCK = 64 * DUO_PAIRS;
 // rounded down to a multiple of 8, is redistributed by setmaxnreg: consumer + producer = 2 x allocation).  Up to three
 // components the stepper fits 104 registers (SRA) and three blocks are resident; beyond that it would spill, so two
 // blocks with 168/88.  The SRI stepper is 2.4 times the generator's work, so its producers wait most of the time and
-// can live with spills: 112/48 (SRI-Lorenz +11 %, Duffing +1.5 %); for SRA, where both roles are equally loaded, 112/48
-// and the two-block splits are 5-8 % slower.  The macros override.
-template <int N, bool ADDITIVE>
+// can live with spills: 112/48 (SRI-Lorenz +11 %, Duffing +1.5 %), and with three components 120/40 (SRI-Lorenz another
+// +5 %; Duffing -1 %, so two components stay at 112/48) or, when the stepper also carries the jump code, 128/32 (jumpy
+// Lorenz +9 %) — profiles/r02_register_split_ab.log; for SRA, where both roles are equally loaded, 112/48
+// and the two-block splits are 5-8 % slower.  One-component SRI models (geometric Brownian motion) have a single serial
+// FP64 chain per lane and fit 88 registers without spilling: four blocks with 88/40 (+10 %, profiles/r02_blocks4_ab.log;
+// two components already spill there: Duffing -3.5 %).  The macros override.
+template <int N, bool ADDITIVE, bool JUMP = false>
 struct DuoConfig {
 #ifdef JSDE_DUO_MIN_BLOCKS
 	static constexpr int BLOCKS = JSDE_DUO_MIN_BLOCKS;
 #else
-	static constexpr int BLOCKS = N <= 3 ? 3 : 2;
+	static constexpr int BLOCKS = (N == 1 && !ADDITIVE) ? 4 : N <= 3 ? 3 : 2;
 #endif
 #ifdef JSDE_DUO_CONSUMER_REGS
 	static constexpr int CONSUMER_REGS = JSDE_DUO_CONSUMER_REGS;
 #else
-	static constexpr int CONSUMER_REGS = N <= 3 ? (ADDITIVE ? 104 : 112) : 168;
+	static constexpr int CONSUMER_REGS = (N == 1 && !ADDITIVE) ? 88 : N <= 3 ? (ADDITIVE ? 104 : N == 3 ? (JUMP ? 128 : 120) : 112) : 168;
 #endif
 #ifdef JSDE_DUO_PRODUCER_REGS
 	static constexpr int PRODUCER_REGS = JSDE_DUO_PRODUCER_REGS;
 #else
-	static constexpr int PRODUCER_REGS = N <= 3 ? (ADDITIVE ? 56 : 48) : 88;
+	static constexpr int PRODUCER_REGS = (N == 1 && !ADDITIVE) ? 40 : N <= 3 ? (ADDITIVE ? 56 : N == 3 ? (JUMP ? 32 : 40) : 48) : 88;
 #endif
 };
 #ifndef JSDE_DUO_STAGE_AHEAD

@@ -71,7 +71,7 @@ constexpr size_t duo_smem_bytes() { return ((size_t)DUO_PAIRS * PairLayout<Model
 // SM's consumer and producer visible to the SM that continues the trajectory.  Exchanges conserve trajectory numbers
 // whatever the interleaving: a lane that finds a slot emptied by a concurrent pop (-1) takes its deposit back.
 template <class Model, bool GRID, bool RECYCLE>
-__global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE>::BLOCKS) k_integrate(EnsembleView e, Controller c, double target, int use_tape,
+__global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE, Model::HAS_JUMP>::BLOCKS) k_integrate(EnsembleView e, Controller c, double target, int use_tape,
 	const double *__restrict__ grid_times_, int grid_count, double *__restrict__ grid_out)
 {
 	constexpr int N = Model::N;
@@ -83,14 +83,14 @@ __global__ void __launch_bounds__(DUO_BLOCK, DuoConfig<Model::N, Model::ADDITIVE
 	double *pair_smem = jsde_smem + MATH_TAB_DOUBLES + pair * PairLayout<N>::DOUBLES;
 
 	if (warp >= DUO_PAIRS) {  // ---- producer warpgroup ----
-		setmaxnreg_dec<DuoConfig<N, Model::ADDITIVE>::PRODUCER_REGS>();
+		setmaxnreg_dec<DuoConfig<N, Model::ADDITIVE, Model::HAS_JUMP>::PRODUCER_REGS>();
 		PairProducer<N, rng_tail<Model>> P(pair_smem, jsde_smem, pair, e.mt);
 		P.run(e.rng_spill, e.rng_level, e.mt_chunk, e.B);
 		return;
 	}
 
 	// ---- consumer warpgroup ----
-	setmaxnreg_inc<DuoConfig<N, Model::ADDITIVE>::CONSUMER_REGS>();
+	setmaxnreg_inc<DuoConfig<N, Model::ADDITIVE, Model::HAS_JUMP>::CONSUMER_REGS>();
 	const double *grid_times = GRID ? grid_times_ : nullptr;  // compile-time nullptr keeps the plain kernel free of grid code
 	// Sampling-grid mode (grid_times != nullptr): the lane integrates to grid_times[0], records its state in
 	// grid_out[0][·][k], goes on to grid_times[1], … — exactly the sequence of integrate() calls of
