@@ -1,6 +1,6 @@
 // extern "C" boundary (include/jsde.h) for WIDE models (one thread block per group of trajectories, wide.cuh).  Same ABI
 // as jsde_abi.cu (shared plumbing: abi_common.cuh), including the single-step surface and pin_noise; what the wide path
-// does not implement (per-trajectory control parameters, the generator debug stream) returns JSDE_E_STATE with a message.
+// does not implement (the generator debug stream) returns JSDE_E_STATE with a message.
 // Must be compiled with -fmad=false.
 #include "glibc_math.h"
 #include "wide.cuh"
@@ -23,6 +23,7 @@ struct jsde_handle : HandleBase {
 	int tpb = 1;  // trajectories per thread block (wide.cuh)
 	WideView v{};
 	double *staging = nullptr;  // [B][n]: host-supplied per-trajectory vectors (step sizes, jump amplitudes, masks)
+	double *par_rows = nullptr;  // [B][NPAR] per-trajectory control parameters (allocated on first use)
 };
 
 namespace {
@@ -159,6 +160,7 @@ int jsde_create(jsde_t **out, int device, int64_t B, int noise_capacity)
 	ALLOC(h->seeds, B); ALLOC(h->par, Model::NPAR > 0 ? Model::NPAR : 1); ALLOC(h->shift, n);
 #undef ALLOC
 	v.par = h->par;
+	v.par_stride = 0;
 	v.dmma = 0;
 	if (const char *env = getenv("JSDE_WIDE_COUPLING"))  // development knob; the API is jsde_set_option
 		v.dmma = Model::UNITS > 0 && !strcmp(env, "dmma");
@@ -238,13 +240,21 @@ int jsde_set_parameters(jsde_t *h, const double *params_host, int per_trajectory
 {
 	if (!h || (Model::NPAR > 0 && !params_host))
 		return fail(JSDE_E_ARG, "Wrong input.");
-	if (per_trajectory)
-		return unsupported("per-trajectory control parameters");
 	if (Model::NPAR == 0)
 		return JSDE_OK;
 	int rc = bind(h);
 	if (rc) return rc;
-	CU(cudaMemcpyAsync(h->par, params_host, Model::NPAR * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	if (!per_trajectory) {
+		CU(cudaMemcpyAsync(h->par, params_host, Model::NPAR * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+		h->v.par = h->par;
+		h->v.par_stride = 0;
+	} else {  // one row per trajectory, used in place: a block reads the rows of its own trajectories
+		if (!h->par_rows && (rc = dev_alloc(h, &h->par_rows, (size_t)h->B * Model::NPAR)))  // allocated once, reused by later calls
+			return rc;
+		CU(cudaMemcpyAsync(h->par_rows, params_host, (size_t)h->B * Model::NPAR * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+		h->v.par = h->par_rows;
+		h->v.par_stride = Model::NPAR;
+	}
 	CU(cudaStreamSynchronize(h->stream));
 	return JSDE_OK;
 }
@@ -601,6 +611,8 @@ int jsde_checkpoint_restore(jsde_t *h, const void *blob_host, int64_t bytes)
 	h->ctrl = hd.ctrl;
 	h->first_step = hd.first_step;
 	h->seed_dirty = false;
+	h->v.par = h->par;  // shared parameters are part of the checkpoint; per-trajectory ones are set again by the caller
+	h->v.par_stride = 0;
 	return restore_sections(h, checkpoint_sections(h), in + sizeof(hd));
 }
 

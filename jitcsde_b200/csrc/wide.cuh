@@ -69,6 +69,7 @@ struct WideView {
 	int *status;
 	unsigned long long *accepted, *rejected;
 	const double *par;
+	int64_t par_stride;  // 0: one parameter set for all trajectories; NPAR: one row per trajectory ([B][NPAR])
 	CallTotals *totals;
 	// scratch vectors [B][n], L2-resident: stage argument, Wiener increments DW/DZ of the current attempt, first drift
 	// (times h), proposal
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 					const double xi = e.generated_jumps ? jsde_jump_xi(e.jump_seed, e.jump_first + b, tape_pos) : e.xis[b * e.tape_len + tape_pos];
 					double *const change = e.sNY + b * N;
 					for (int i = lane; i < N; i += 32)
-						change[i] = Model::jump_component(i, t, Ycur, xi, e.par);
+						change[i] = Model::jump_component(i, t, Ycur, xi, e.par + b * e.par_stride);
 					__syncwarp();
 					for (int i = lane; i < N; i += 32)
 						Ycur[i] += change[i];
@@ -470,9 +471,9 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 					if (!jump_set) {  // next_jump property (:682-687): t + IJI(t, y)
 						double wait = __longlong_as_double(0x7ff0000000000000LL);  // past the end of a tape: no further jumps
 						if (e.generated_jumps)
-							wait = Model::waiting_time(t, Ycur, jsde_jump_tau(e.jump_seed, e.jump_first + b, tape_pos), e.par);
+							wait = Model::waiting_time(t, Ycur, jsde_jump_tau(e.jump_seed, e.jump_first + b, tape_pos), e.par + b * e.par_stride);
 						else if (tape_pos < e.tape_len)
-							wait = Model::waiting_time(t, Ycur, e.taus[b * e.tape_len + tape_pos], e.par);
+							wait = Model::waiting_time(t, Ycur, e.taus[b * e.tape_len + tape_pos], e.par + b * e.par_stride);
 						else
 							exhausted = true;  // reported (jsde_stats.n_tape_exhausted): this trajectory's jump process ends here
 						next_jump = t + wait;
@@ -817,12 +818,12 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 						if (i < N) {
 							const double cs = (UNITS > 0 && i < UNITS) ? SC[i * TPAD + col] : 0.0;
 							const double I10 = (e.sW[b * N + i] + e.sZ[b * N + i] * (1. / 1.7320508075688772)) * (h / 2.);
-							const double fh1 = Model::drift_local(i, t, Y, e.par, cs) * h;
+							const double fh1 = Model::drift_local(i, t, Y, e.par + b * e.par_stride, cs) * h;
 							if constexpr (Model::ADDITIVE) {
-								const double g1 = Model::diffusion_component(i, t + h, Y, e.par);
+								const double g1 = Model::diffusion_component(i, t + h, Y, e.par + b * e.par_stride);
 								av[cc] = Y[i] + 0.75 * fh1 + 0.5 * g1 * I10 / h;
 							} else {  // SRIW1 (template:417-438): the arguments of fh2, g2 and g3 only need fh1 and g1
-								const double g1 = Model::diffusion_component(i, t, Y, e.par);
+								const double g1 = Model::diffusion_component(i, t, Y, e.par + b * e.par_stride);
 								const double sqh = sqrt(h);
 								av[cc] = Y[i] + 0.75 * fh1 + 1.5 * g1 * I10 / h;
 								aAv[cc] = Y[i] + 0.25 * fh1 + 0.5 * g1 * sqh;
@@ -861,9 +862,9 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 							const int i = cc * WBLOCK + tid;
 							g2v[cc] = g3v[cc] = aCv[cc] = 0.0;
 							if (i < N) {
-								const double g1 = Model::diffusion_component(i, t, Y, e.par);
-								g2v[cc] = Model::diffusion_component(i, t + 0.25 * h, e.argA + b * N, e.par);
-								g3v[cc] = Model::diffusion_component(i, t + h, e.argB + b * N, e.par);
+								const double g1 = Model::diffusion_component(i, t, Y, e.par + b * e.par_stride);
+								g2v[cc] = Model::diffusion_component(i, t + 0.25 * h, e.argA + b * N, e.par + b * e.par_stride);
+								g3v[cc] = Model::diffusion_component(i, t + h, e.argB + b * N, e.par + b * e.par_stride);
 								aCv[cc] = Y[i] + 0.25 * e.sF1[b * N + i] + sqh * (-5 * g1 + 3 * g2v[cc] + 0.5 * g3v[cc]);
 							}
 						}
@@ -898,17 +899,17 @@ __global__ void __launch_bounds__(WBLOCK, WBLOCKS_PER_SM) k_wide_integrate(WideV
 							const double W = e.sW[b * N + i];
 							const double I10 = (W + e.sZ[b * N + i] * (1. / 1.7320508075688772)) * (h / 2.);
 							const double fh1 = e.sF1[b * N + i];
-							const double fh2 = Model::drift_local(i, t_mid, A, e.par, cs) * h;
+							const double fh2 = Model::drift_local(i, t_mid, A, e.par + b * e.par_stride, cs) * h;
 							double E_N, ny;
 							if constexpr (Model::ADDITIVE) {
-								const double g1 = Model::diffusion_component(i, t + h, Y, e.par);
-								const double g2 = Model::diffusion_component(i, t, Y, e.par);
+								const double g1 = Model::diffusion_component(i, t + h, Y, e.par + b * e.par_stride);
+								const double g2 = Model::diffusion_component(i, t, Y, e.par + b * e.par_stride);
 								E_N = I10 / h * (g2 - g1);
 								ny = Y[i] + E_N + (1. / 3.) * (fh1 + 2 * fh2) + W * g1;
 							} else {  // SRIW1 (template:447-464), expression shapes of stepper.cuh
-								const double g1 = Model::diffusion_component(i, t, Y, e.par);
+								const double g1 = Model::diffusion_component(i, t, Y, e.par + b * e.par_stride);
 								const double g2 = e.sG2[b * N + i], g3 = e.sG3[b * N + i];
-								const double g4 = Model::diffusion_component(i, t + 0.25 * h, e.argC + b * N, e.par);
+								const double g4 = Model::diffusion_component(i, t + 0.25 * h, e.argC + b * N, e.par + b * e.par_stride);
 								const double sqh = sqrt(h);
 								const double third_over_h = 1. / h / 3.;
 								const double I11s = (W * W - h) * 0.5 / sqh;

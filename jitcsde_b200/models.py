@@ -76,7 +76,7 @@ validation_exp = ModelSpec("validation_exp", 1, False, ("-(y(0)*y(0)*y(0))+4*y(0
 pendulum = ModelSpec("pendulum", 2, False, ("y(1)", "-sin(y(0))-0.1*y(1)"), ("0.0", "0.2+0.1*cos(y(0))"))
 
 
-def fhn_network(units: int, name: str, seed: int = 7, multiplicative: bool = False, jumpy: bool = False) -> ModelSpec:
+def fhn_network(units: int, name: str, seed: int = 7, multiplicative: bool = False, jumpy: bool = False, pars: bool = False) -> ModelSpec:
 	"""
 	Noisy FitzHugh–Nagumo network with dense coupling (SURVEY §8 d config 5; units=500 gives n=1000):
 	    dv_i = v_i - v_i^3/3 - w_i + I + (K/N) sum_j A_ij (v_j - v_i),    dw_i = eps (v_i + a - b w_i),
@@ -97,14 +97,18 @@ JSDE_MODEL_CONST double FHN_AT[FHN_UNITS * FHN_UNITS] = {{{table}}};
 """
 	f_component = ("(i < FHN_UNITS ? y(i) - y(i) * y(i) * y(i) / 3.0 - y(FHN_UNITS + i) + 0.5 + (1.0 / FHN_UNITS) * coupling"
 		" : 0.08 * (y(i - FHN_UNITS) + 0.7 - 0.8 * y(i)))")
+	if pars:  # control parameters (shared or one set per trajectory): input current, coupling strength, noise amplitude
+		f_component = f_component.replace("+ 0.5 +", "+ I_ext +").replace("(1.0 / FHN_UNITS)", "(K_c / FHN_UNITS)")
 	# multiplicative variant (exercises the wide SRI path): state-dependent amplitudes, one of them reaching across
 	# components — the diffusion of w_i depends on v_i
 	g_component = ("(i < FHN_UNITS ? 0.05 * y(i) + 0.02 : 0.01 * y(i - FHN_UNITS) + 0.01 * y(i))" if multiplicative
 		else "(i < FHN_UNITS ? 0.05 : 0.0)")
+	if pars:
+		g_component = g_component.replace("0.05", "sigma")
 	# jumpy variant (exercises jumps on the wide path): kicks on the v components, intensity growing with v_0^2
 	jump = JumpSpec(("(i < FHN_UNITS ? 0.2 * xi * (1.0 + y(i)) : 0.0)",), iji="tau/(2.0+y(0)*y(0))") if jumpy else None
 	return ModelSpec(name, 2 * units, not multiplicative, (), (), preamble=preamble,
-		f_component=f_component, g_component=g_component, jump=jump,
+		f_component=f_component, g_component=g_component, jump=jump, control_pars=("I_ext", "K_c", "sigma") if pars else (),
 		coupling_units=units, coupling_table="FHN_AT")
 
 
@@ -112,6 +116,7 @@ JSDE_MODEL_CONST double FHN_AT[FHN_UNITS * FHN_UNITS] = {{{table}}};
 fhn_small = fhn_network(24, "fhn_small")
 fhn_small_mult = fhn_network(24, "fhn_small_mult", multiplicative=True)
 fhn_small_jumpy = fhn_network(24, "fhn_small_jumpy", jumpy=True)
+fhn_small_pars = fhn_network(24, "fhn_small_pars", pars=True)
 _FHN_1000 = None
 
 
@@ -125,5 +130,5 @@ def fhn_1000() -> ModelSpec:
 
 ALL = {m.name: m for m in (
 	lorenz_additive, lorenz_additive_fixture, lorenz_multiplicative, lorenz_jumpy, lorenz_jumpy_rate,
-	gbm, gbm_pars, duffing, ou, ou_timedep, cubic, ring6, ring6_mult, validation_exp, pendulum, fhn_small, fhn_small_mult, fhn_small_jumpy,
+	gbm, gbm_pars, duffing, ou, ou_timedep, cubic, ring6, ring6_mult, validation_exp, pendulum, fhn_small, fhn_small_mult, fhn_small_jumpy, fhn_small_pars,
 )}

@@ -159,6 +159,43 @@ def test_wide_failure_paths_and_unsupported_calls():
 		E.integrate_jumps(1.0, np.ones((4, 2)), np.ones((4, 2)))
 
 
+@pytest.mark.parametrize("tpb", [1, 4, 7])
+def test_wide_control_parameters_shared_and_per_trajectory(monkeypatch, tpb):
+	"""set_parameters on the wide path (reference: jitced_template.c set_parameters / `_jitcsde.py` control_pars): one set for
+	the ensemble, then one row per trajectory (a block reads the rows of its own trajectories), then shared again"""
+	monkeypatch.setenv("JSDE_WIDE_TPB", str(tpb))
+	spec, B, T = models.fhn_small_pars, 10, 0.3
+	y0 = np.random.default_rng(5).random((B, spec.n))
+	seeds = np.arange(B, dtype=np.uint32) + 11
+	E = Ensemble(spec, B)
+
+	def run_with(pars, per_trajectory):
+		E.seed(seeds)
+		E.set_state(y0, 0.0)
+		E.set_integration_parameters(ControllerParameters())
+		E.set_parameters(pars)
+		E.integrate(T)
+		rows = pars if per_trajectory else np.tile(pars, (B, 1))
+		got = E.get_state()
+		for k in range(B):
+			P = port.PortCore(spec, y0[k], 0.0, int(seeds[k]))
+			P.set_parameters(*rows[k])
+			assert_bits_equal(got[k], P.integrate(T), f"trajectory {k}")
+		return got
+
+	shared = run_with(np.array([0.5, 1.0, 0.05]), False)
+	# with these values the model is fhn_small itself
+	ref = port.run_ensemble(models.fhn_small, y0, seeds, 0.0, T)
+	assert_bits_equal(shared, ref["y"], "parameters equal to the constants of fhn_small")
+	rng = np.random.default_rng(9)
+	rows = np.column_stack([rng.uniform(0.3, 0.7, B), rng.uniform(0.5, 2.0, B), rng.uniform(0.02, 0.08, B)])
+	individual = run_with(rows, True)
+	assert not np.array_equal(individual, shared)
+	for _ in range(3):  # repeated per-trajectory uploads reuse their buffer
+		E.set_parameters(rows)
+	assert_bits_equal(run_with(np.array([0.5, 1.0, 0.05]), False), shared, "shared again")
+
+
 @pytest.mark.parametrize("name,tpb", [("fhn_small", 1), ("fhn_small", 7), ("fhn_small_mult", 4)])
 def test_wide_single_step_surface_vs_oracle(monkeypatch, name, tpb):
 	"""the reference core's own methods (jitced_template.c:252-267, 396-545) on the wide path, call by call against the
@@ -262,17 +299,42 @@ def test_wide_moments():
 	np.testing.assert_allclose(got[1 + spec.n:], (y ** 2).sum(axis=0), rtol=1e-12)
 
 
+def symbolic_network(units, B, current=0.5, amplitude=0.05, control_pars=()):
+	"""a user's Python-loop FitzHugh–Nagumo network through the public constructor (also used by tools/prebuild_test_models.py)"""
+	import sympy
+	from jitcsde_b200 import jitcsde, y
+	A = np.random.default_rng(7).random((units, units))
+	fs = [y(i) - y(i) ** 3 / 3 - y(units + i) + current + sum(float(A[i, j]) / units * (y(j) - y(i)) for j in range(units)) for i in range(units)]
+	fs += [0.08 * (y(i) + 0.7 - 0.8 * y(units + i)) for i in range(units)]
+	gs = [sympy.sympify(amplitude)] * units + [sympy.Float(0.0)] * units
+	return jitcsde(fs, gs, ensemble=B, control_pars=control_pars, verbose=False)
+
+
+def test_symbolic_network_with_per_trajectory_parameters():
+	"""control parameters of a symbolic wide model, one set per trajectory, through the front end"""
+	import sympy
+	units, B, T = 20, 6, 0.3
+	I_ext, sigma = sympy.symbols("I_ext sigma")
+	SDE = symbolic_network(units, B, I_ext, sigma, control_pars=[I_ext, sigma])
+	assert SDE.spec.wide and SDE.spec.coupling_units == units and SDE.spec.control_pars == ("I_ext", "sigma")
+	y0 = sharding.global_initial_states(0, B, 2 * units)
+	seeds = sharding.global_seeds(0, B)
+	pars = np.column_stack([np.linspace(0.3, 0.7, B), np.linspace(0.02, 0.08, B)])
+	SDE.set_seed(seeds)
+	SDE.set_initial_value(y0, 0.0)
+	SDE.set_parameters(pars)
+	out = SDE.integrate(T)
+	for k in range(B):
+		P = port.PortCore(SDE.spec, y0[k], 0.0, int(seeds[k]))
+		P.set_parameters(*pars[k])
+		assert_bits_equal(out[k], P.integrate(T), f"trajectory {k}")
+
+
 def test_symbolic_network_through_the_front_end():
 	"""a user's Python-loop network (n = 96) goes through the symbolic front end onto the wide path; bit-identical to the
 	oracle's build of the same generated expressions, and statistically the same SDE as the hand-written model"""
-	import sympy
-	from jitcsde_b200 import jitcsde, y
 	units, B, T = 48, 11, 0.4
-	A = np.random.default_rng(7).random((units, units))
-	fs = [y(i) - y(i) ** 3 / 3 - y(units + i) + 0.5 + sum(float(A[i, j]) / units * (y(j) - y(i)) for j in range(units)) for i in range(units)]
-	fs += [0.08 * (y(i) + 0.7 - 0.8 * y(units + i)) for i in range(units)]
-	gs = [sympy.Float(0.05)] * units + [sympy.Float(0.0)] * units
-	SDE = jitcsde(fs, gs, ensemble=B, verbose=False)
+	SDE = symbolic_network(units, B)
 	assert SDE.spec.wide and SDE.spec.coupling_units == units
 	y0 = sharding.global_initial_states(0, B, 2 * units)
 	SDE.set_seed(sharding.global_seeds(0, B))

@@ -11,3 +11,8 @@ for name, factory in {**S.MULTIPLICATIVE, **S.ADDITIVE}.items():
 for options in (dict(simplify=False), dict(do_cse=True), dict(simplify=True)):
 	print(options, os.path.relpath(S.MULTIPLICATIVE["default"]().compile_C(**options), ROOT))
 print("jumpy", os.path.relpath(S.jumpy().compile_C(), ROOT))
+import sympy
+import test_gpu_wide as W
+print("symbolic network", os.path.relpath(W.symbolic_network(48, 11).compile_C(), ROOT))
+I_ext, sigma = sympy.symbols("I_ext sigma")
+print("symbolic network with parameters", os.path.relpath(W.symbolic_network(20, 6, I_ext, sigma, control_pars=[I_ext, sigma]).compile_C(), ROOT))
