@@ -14,13 +14,14 @@ constexpr int BLOCK = 128;  // single-step kernels: one trajectory per thread
 // Who computes the scale-independent Gaussian factor s = sqrt(-2 log(r2)/r2) (warp_rng.cuh: TAIL): the stepper (default) or
 // the generator side.  One choice per model library — queue contents must mean the same to every kernel.  Round 2 measured
 // the generator-side variant (the idea: for multiplicative-noise models the producer warps idle more than half of the time):
-// SRI-Lorenz -2.4 %, Duffing +2.2 %, additive Lorenz -17 % (profiles/r02_tail_in_producer_ab.log) — bit-identical results
-// either way (the parity suite passes in both settings), so it stays a build-time knob and is off.
+// additive Lorenz -17 %, and with the final register splits SRI-Lorenz -4 %, jumpy Lorenz -11 %, geometric Brownian motion
+// -6.5 %, stochastic Duffing +3.6 % (profiles/r02_tail_in_producer_ab.log) — bit-identical results either way (the parity
+// suite passes in both settings).  It is on where it pays: two-component SRI models, whose producers keep 48 registers.
 #ifndef JSDE_RNG_TAIL
-#define JSDE_RNG_TAIL(additive) false
+#define JSDE_RNG_TAIL(additive, n) (!(additive) && (n) == 2)
 #endif
 template <class Model>
-constexpr bool rng_tail = JSDE_RNG_TAIL(Model::ADDITIVE);
+constexpr bool rng_tail = JSDE_RNG_TAIL(Model::ADDITIVE, Model::N);
 template <class Model>
 using ModelRng = WarpRng<Model::N, rng_tail<Model>>;
 

@@ -27,7 +27,16 @@
 namespace jsde {
 
 constexpr int RNG_GROUP = 8;     // candidates per trajectory per op
-constexpr int RNG_STRIDE = 33;   // row stride (doubles) of the FIFO arrays: conflict-free column writes
+// Row stride (doubles) of the FIFO arrays [slot][lane].  Element (s, T) lies in bank pair (s + T) mod 16: the producer's
+// compacted writes of ONE trajectory (same T, consecutive slots) never collide; the writes of the four trajectories of a
+// slot can, and so can the consumer's pops when the lanes' read slots differ (ncu, profiles/r02_headline_sra_sliced_*:
+// pops 2.4 wavefronts per instruction instead of 2, FIFO writes 1.8 times the ideal).  A stride of 32 makes the pops
+// conflict-free and the writes eight-way conflicted: measured slower (profiles/r02_fifo_stride_ab.log).  Shared-memory
+// wavefronts are not what limits the kernel (LSU data pipe 53 % busy, issue slots 69 %).
+#ifndef JSDE_RNG_STRIDE
+#define JSDE_RNG_STRIDE 33
+#endif
+constexpr int RNG_STRIDE = JSDE_RNG_STRIDE;
 
 // 16-byte asynchronous copy global -> shared (LDGSTS): no register, no scoreboard wait until cp.async.wait_group
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
